@@ -1,0 +1,154 @@
+"""Generates the golden fixtures in this directory by running the UNMODIFIED reference
+(/root/reference, ducha-aiki/affnet @ da7cf51) on CPU in the build container.
+
+    python tests/golden/make_golden.py
+
+The reference pins no results of its own (no tests, no golden vectors - SURVEY.md §4), so these
+files are what pins `oracle/affnet_oracle.py` to the reference.  Re-run only when the reference
+changes.  Outputs (all .npz, compressed):
+
+  weights.npz        state dicts of pretrained/AffNet.pth, pretrained/OriNet.pth, HardNet++.pth
+  graf_crop.npz      256x320 crop of test-graf/img1.png, K=300: per-stage intermediates
+  graf_full.npz      full test-graf/img1.png 800x640, K=2000, do_ori in {False, True}: final outputs
+  nms_q4.npz         NMS3dAndComposeA on synthetic response maps with a non-trivial octave map (Q4)
+  face_patches.npz   first 64 patches of examples/just_shape/img/face.png -> AffNetFast matrices
+  nets_random.npz    the three nets on 32 random patches (input + outputs)
+"""
+import contextlib
+import io
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
+import ref_harness as R  # noqa: E402
+
+warnings.filterwarnings("ignore")
+torch.set_num_threads(8)
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def save(name, **kw):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **{k: (v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in kw.items()})
+    print(name, "%.1f KB" % (os.path.getsize(path) / 1024.0))
+
+
+def rgb_of(path):
+    from PIL import Image
+    return np.array(Image.open(path).convert("RGB"))
+
+
+def gray_of(rgb):
+    return torch.from_numpy(np.mean(rgb, axis=2).astype(np.float32)).view(1, 1, rgb.shape[0], rgb.shape[1])
+
+
+def main():
+    m = R.ref_modules()
+    aff, ori, hn = R.load_nets()
+    w = {}
+    for pre, net in (("affnet", aff), ("orinet", ori), ("hardnet", hn)):
+        for k, v in net.state_dict().items():
+            if "num_batches_tracked" not in k:
+                w[pre + "/" + k] = v
+    save("weights.npz", **w)
+
+    # ---------------- graf crop, per-stage --------------------------------------------------
+    rgb = rgb_of(R.REF + "/test-graf/img1.png")
+    crop = np.ascontiguousarray(rgb[100:356, 200:520])
+    img = gray_of(crop)
+    K = 300
+    out = dict(rgb=crop, K=K)
+    det = R.make_detector(aff, ori, num_features=K)
+    with torch.no_grad(), quiet():
+        resp, LAFs, pidx, lidx = det.multiScaleDetector(img, int(1.5 * K))
+        pyr = det.scale_pyr
+        out["n_oct"] = len(pyr)
+        for o in range(len(pyr)):
+            for l in range(5):
+                out["pyr_sum_%d_%d" % (o, l)] = pyr[o][l].double().sum()
+        out["pyr_1_2"] = pyr[1][2][0, 0]
+        out["pyr_0_4_rows"] = pyr[0][4][0, 0, 100:108]
+        out["hess_1_2"] = det.RespNet(pyr[1][2], det.sigmas[1][2])[0, 0]
+        out.update(det_resp=resp, det_LAFs=LAFs, det_pidx=pidx, det_lidx=lidx)
+        L2 = LAFs.clone()
+        L2[:, 0:2, 0:2] = det.mrSize * L2[:, :, 0:2]
+        inv = m["LAF"].get_inverted_pyr_index(pyr, pidx, lidx)
+        P = m["LAF"].extract_patches_from_pyramid_with_inv_index(pyr, inv, L2, PS=32)
+        A = m["Utils"].batched_forward(aff, P, 256)
+        out.update(aff_patches=P[:64], aff_A=A)
+        r2, L3, p2, l2 = det.getAffineShape(resp, L2, pidx, lidx, K)
+        out.update(shape_resp=r2, shape_LAFs=L3, shape_pidx=p2, shape_lidx=l2)
+        inv = m["LAF"].get_inverted_pyr_index(pyr, p2, l2)
+        P = m["LAF"].extract_patches_from_pyramid_with_inv_index(pyr, inv, L3, PS=32)
+        Rm = ori(P)
+        out.update(ori_patches=P[:64], ori_R=Rm)
+        for do_ori in (False, True):
+            d = R.make_detector(aff, ori, num_features=K)
+            dL, rr, pp, dd = R.run_full(d, hn, img, do_ori)
+            o_, l_ = m["LAF"].get_pyramid_and_level_index_for_LAFs(dL, d.sigmas, d.pix_dists, 32)
+            tag = "ori" if do_ori else "noori"
+            out.update({tag + "_dLAFs": dL, tag + "_resp": rr, tag + "_desc_patches": pp[:64], tag + "_desc": dd,
+                        tag + "_desc_oct": o_, tag + "_desc_lvl": l_})
+    save("graf_crop.npz", **out)
+
+    # ---------------- graf full, final outputs only ----------------------------------------
+    img = gray_of(rgb)
+    out = dict(rgb=rgb, K=2000)
+    for do_ori in (False, True):
+        d = R.make_detector(aff, ori, num_features=2000)
+        dL, rr, pp, dd = R.run_full(d, hn, img, do_ori)
+        tag = "ori" if do_ori else "noori"
+        out.update({tag + "_dLAFs": dL, tag + "_resp": rr, tag + "_desc": dd.half()})
+    with torch.no_grad(), quiet():
+        rall, _, pa, la = d.multiScaleDetector(img, -1)
+    out["cand_counts"] = np.array([[int(((pa == o) & (la == l)).sum()) for l in range(3)] for o in range(len(d.scale_pyr))])
+    save("graf_full.npz", **out)
+
+    # ---------------- NMS with octave map (Q4) ---------------------------------------------
+    g = torch.Generator().manual_seed(7)
+    h, wd = 40, 56
+    base = torch.rand(1, 1, h, wd, generator=g)
+    import torch.nn.functional as F
+    maps = []
+    for i in range(3):
+        x = torch.rand(1, 1, h, wd, generator=g) * 400.0
+        x = F.avg_pool2d(F.pad(x, (1, 1, 1, 1), "replicate"), 3, stride=1)
+        maps.append(x.contiguous())
+    omap = (torch.rand(h, wd, generator=g) * 4.3).byte().view(1, 1, h, wd)  # values 0..4
+    omap[0, 0, :, : wd // 2] = 0
+    scales = [1.6, 2.0158736798317967, 2.5398416831491195]
+    out = dict(low=maps[0][0, 0], cur=maps[1][0, 0], high=maps[2][0, 0], omap=omap[0, 0], scales=np.array(scales))
+    for nf, tag in ((0, "all"), (20, "top20")):
+        nms = m["HandCraftedModules"].NMS3dAndComposeA(w=wd, h=h, border=5, mrSize=5.192)
+        with torch.no_grad():
+            r, A, om2 = nms(maps[0].clone(), maps[1].clone(), maps[2].clone(), num_features=nf, octaveMap=omap.clone(), scales=scales)
+        out.update({tag + "_resp": r, tag + "_LAFs": A, tag + "_omap": om2[0, 0]})
+    save("nms_q4.npz", **out)
+
+    # ---------------- just_shape: face patches -> AffNet ----------------------------------
+    import cv2
+    face = cv2.imread(R.REF + "/examples/just_shape/img/face.png", 0)
+    wdt = face.shape[1]
+    pts = np.stack([cv2.resize(face[i * wdt:(i + 1) * wdt], (32, 32), interpolation=cv2.INTER_LINEAR) for i in range(64)])
+    P = torch.from_numpy(pts.astype(np.float32) / 255.0).view(64, 1, 32, 32)
+    with torch.no_grad():
+        A = aff(P)
+    save("face_patches.npz", patches_u8=pts, A=A)
+
+    # ---------------- nets on random patches ----------------------------------------------
+    P = torch.rand(32, 1, 32, 32, generator=g) * 255.0
+    with torch.no_grad():
+        save("nets_random.npz", patches=P, affnet_A=aff(P), orinet_R=ori(P), orinet_angle=ori(P, return_rot_matrix=False),
+             hardnet_desc=hn(P))
+
+
+if __name__ == "__main__":
+    main()

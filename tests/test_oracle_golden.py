@@ -1,0 +1,150 @@
+"""CPU tests: pin oracle/affnet_oracle.py against golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py).  Tolerances are stated per stage."""
+import numpy as np
+import pytest
+import torch
+
+import affnet_oracle as O
+from helpers import gold, load_weights, gray_from_rgb, match_keypoints
+
+W = load_weights()
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_gauss_kernel_sizes_q1():
+    # sigma -> (k, pad)
+    for s, k in ((1.5199, 11), (1.2263, 9), (1.5450, 11), (1.9466, 13), (2.4525, 15)):
+        assert O.gauss_kernel_size(s) == k
+    g = O.gauss_kernel_1d(1.2263)
+    assert abs(np.outer(g, g) - O.gauss_kernel_2d(1.2263)).max() < 1e-16   # separable to f64 rounding
+
+
+def test_pyramid_plan_graf():
+    sizes, bs, sig, pix = O.pyramid_plan(640, 800)
+    assert sizes == [(640, 800), (320, 400), (160, 200), (80, 100), (40, 50), (20, 25)]
+    assert sig[0][3] == 3.1999999999999997 and pix[3] == [8.0] * 5
+    assert abs(bs[0][0] - 1.5198684) < 1e-6 and [O.gauss_kernel_size(s) for s in bs[0][1:]] == [9, 11, 13, 15]
+
+
+def test_detector_stage_bit_exact_vs_reference_golden():
+    z = gold("graf_crop.npz")
+    img = gray_from_rgb(z["rgb"])
+    K = int(z["K"])
+    pyr, sig, pix = O.scale_pyramid(img)
+    assert len(pyr) == int(z["n_oct"])
+    for o in range(len(pyr)):
+        for l in range(5):
+            assert abs(pyr[o][l].double().sum().item() - float(z["pyr_sum_%d_%d" % (o, l)])) < 1e-6
+    assert torch.equal(pyr[1][2][0, 0], T(z["pyr_1_2"]))          # same torch op => bit exact
+    assert torch.equal(pyr[0][4][0, 0, 100:108], T(z["pyr_0_4_rows"]))
+    assert torch.equal(O.hessian_response(pyr[1][2], sig[1][2])[0, 0], T(z["hess_1_2"]))
+    resp, LAFs, pidx, lidx = O.multi_scale_detector(pyr, sig, int(1.5 * K), 5.192)
+    assert torch.equal(resp, T(z["det_resp"]))                     # identical index set and order
+    assert torch.equal(pidx, T(z["det_pidx"])) and torch.equal(lidx, T(z["det_lidx"]))
+    assert (LAFs - T(z["det_LAFs"])).abs().max() < 1e-6            # soft-argmax conv order: 6e-8
+
+
+def test_nms_octave_map_q4():
+    z = gold("nms_q4.npz")
+    low, cur, high = (T(z[k]).view(1, 1, *z[k].shape) for k in ("low", "cur", "high"))
+    for nf, tag in ((0, "all"), (20, "top20")):
+        r, A, om, idxs = O.nms3d_and_compose(low, cur, high, nf, z["omap"].copy(), list(z["scales"]), 5.192)
+        assert torch.equal(r, T(z[tag + "_resp"]))
+        assert (r < 0).any() or nf > 0                             # Q4: re-detected pixels go negative
+        assert np.array_equal(om, z[tag + "_omap"])                # uint8 wrap reproduced
+        assert (A - T(z[tag + "_LAFs"])).abs().max() < 1e-6
+
+
+def test_sampler_and_affnet_stage():
+    z = gold("graf_crop.npz")
+    img = gray_from_rgb(z["rgb"])
+    pyr, sig, pix = O.scale_pyramid(img)
+    L = T(z["det_LAFs"]).clone()
+    L[:, 0:2, 0:2] = 5.192 * L[:, :, 0:2]
+    P = O.extract_patches_from_pyramid(pyr, T(z["det_pidx"]), T(z["det_lidx"]), L, 32)
+    # closed-form f64 bilinear vs torch's fp32 affine_grid+grid_sample: coordinate rounding x gradient
+    assert (P[:64] - T(z["aff_patches"])).abs().max() < 2e-2      # on a 0..255 scale
+    A = O.affnet_forward(T(z["aff_patches"]), W["affnet"])
+    assert (A - T(z["aff_A"])[:64]).abs().max() < 1e-5
+    A_all = O.affnet_forward(P, W["affnet"])
+    assert (A_all - T(z["aff_A"])).abs().max() < 1e-3
+
+
+def test_shape_filter_given_reference_A():
+    z = gold("graf_crop.npz")
+    K = int(z["K"])
+    L = T(z["det_LAFs"]).clone(); L[:, 0:2, 0:2] = 5.192 * L[:, :, 0:2]
+    A = T(z["aff_A"])
+    newL = torch.cat([torch.bmm(A, L[:, :, :2]), L[:, :, 2:]], 2)
+    mask = O.shape_filter_mask(A, newL)
+    resp = T(z["det_resp"])
+    if int(mask.sum()) > K:
+        r, idxs = torch.topk(resp * mask.float(), k=K)
+    else:
+        idxs = mask.nonzero().view(-1); r = resp[idxs]
+    assert torch.equal(r, T(z["shape_resp"]))                      # identical selection given identical A
+    assert (newL[idxs] - T(z["shape_LAFs"])).abs().max() < 1e-6
+
+
+def test_orinet_and_hardnet_stage():
+    z = gold("graf_crop.npz")
+    R = O.orinet_forward(T(z["ori_patches"]), W["orinet"])
+    assert (R - T(z["ori_R"])[:64]).abs().max() < 1e-5
+    d = O.hardnet_forward(T(z["ori_desc_patches"]), W["hardnet"])
+    assert (d - T(z["ori_desc"])[:64]).abs().max() < 1e-5
+
+
+def test_level_selection_a15():
+    z = gold("graf_crop.npz")
+    sizes, bs, sig, pix = O.pyramid_plan(*z["rgb"].shape[:2])
+    for tag in ("noori", "ori"):
+        o, l = O.pyramid_level_for_lafs(T(z[tag + "_dLAFs"]), sig, pix, 32)
+        assert np.array_equal(o.numpy(), z[tag + "_desc_oct"]) and np.array_equal(l.numpy(), z[tag + "_desc_lvl"])
+
+
+def test_nets_on_random_patches_and_face():
+    z = gold("nets_random.npz")
+    P = T(z["patches"])
+    assert (O.affnet_forward(P, W["affnet"]) - T(z["affnet_A"])).abs().max() < 1e-5
+    assert (O.orinet_forward(P, W["orinet"]) - T(z["orinet_R"])).abs().max() < 1e-5
+    assert (O.orinet_angle(P, W["orinet"]) - T(z["orinet_angle"])).abs().max() < 1e-5
+    assert (O.hardnet_forward(P, W["hardnet"]) - T(z["hardnet_desc"])).abs().max() < 1e-5
+    f = gold("face_patches.npz")
+    P = torch.from_numpy(f["patches_u8"].astype(np.float32) / 255.0).view(-1, 1, 32, 32)
+    A = O.affnet_forward(P, W["affnet"])
+    assert (A - T(f["A"])).abs().max() < 1e-5
+    # SURVEY §8c known answers
+    assert abs(A[0, 0, 0] - 0.9761) < 1e-4 and abs(A[0, 1, 0] - 0.0652) < 1e-4 and abs(A[1, 1, 0] - 0.2110) < 1e-4
+
+
+@pytest.mark.parametrize("do_ori", [False, True])
+def test_end_to_end_crop(do_ori):
+    z = gold("graf_crop.npz")
+    img = gray_from_rgb(z["rgb"])
+    tag = "ori" if do_ori else "noori"
+    dL, resp, st = O.detect(img, W["affnet"], W["orinet"], int(z["K"]), do_ori=do_ori)
+    desc, _, _ = O.describe(dL, st, W["hardnet"])
+    gL, gd = T(z[tag + "_dLAFs"]), T(z[tag + "_desc"])
+    ia, ib = match_keypoints(gL, dL)
+    assert len(ia) >= 0.995 * gL.shape[0]
+    assert (gL[ia] - dL[ib]).abs().max() < 2e-2                    # px units; fp32 sampler noise -> AffNet/OriNet
+    assert (gd[ia] - desc[ib]).abs().max() < 5e-3
+
+
+def test_end_to_end_graf_full_known_answers():
+    z = gold("graf_full.npz")
+    img = gray_from_rgb(z["rgb"])
+    dL, resp, st = O.detect(img, W["affnet"], None, 2000, do_ori=False)
+    gL = T(z["noori_dLAFs"])
+    # first LAFs of graf img1
+    assert (gL[0] - torch.tensor([[16.8363, 0, 467.4685], [0.8120, 17.7178, 264.4630]])).abs().max() < 1e-3
+    ia, ib = match_keypoints(gL, dL)
+    assert len(ia) >= 0.995 * 2000
+    assert (gL[ia] - dL[ib]).abs().max() < 2e-2
+    desc, _, _ = O.describe(dL, st, W["hardnet"])
+    assert (T(z["noori_desc"]).float()[ia] - desc[ib]).abs().max() < 5e-3
+    # candidate counts per (octave, level): 7885 in total
+    assert int(z["cand_counts"].sum()) == 7885
