@@ -1,0 +1,76 @@
+"""LAF helpers with the reference's names (LAF.py): the affine sampler, (de)normalisation, level routing and the
+Oxford-ellipse output conversion."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def extract_patches(img, LAFs, PS=32, bs=32):
+    """LAF.py:364-372.  img [1|n,C,h,w] CUDA float32, LAFs [n,2,3] normalised -> [n,C,PS,PS].
+    `bs` (a memory-chunking knob in the reference) is accepted and ignored."""
+    img = L.f32c(img, "img")
+    LAFs = L.f32c(LAFs, "LAFs")
+    n = LAFs.size(0)
+    Cc, h, w = img.size(1), img.size(2), img.size(3)
+    per_patch = 1 if (img.size(0) == n and n != 1) else 0
+    if not per_patch and img.size(0) != 1:
+        raise L.AffnetB200Error("img batch must be 1 or equal to the number of LAFs")
+    out = torch.empty(n, Cc, PS, PS, dtype=torch.float32, device=img.device)
+    step = 65535
+    for s in range(0, n, step):
+        e = min(n, s + step)
+        src = img[s:e] if per_patch else img
+        L.check(L.lib().ag_extract_patches(L.ptr(src), Cc, h, w, per_patch, L.ptr(LAFs[s:e]), e - s, PS, L.ptr(out[s:e]), L.stream_ptr()))
+    return out
+
+
+def _scale(LAFs, ac, xc, yc):
+    LAFs = L.f32c(LAFs, "LAFs")
+    out = torch.empty_like(LAFs)
+    L.check(L.lib().ag_lafs_scale(L.ptr(LAFs), L.ptr(out), LAFs.size(0), ac, xc, yc, L.stream_ptr()))
+    return out
+
+
+def denormalizeLAFs(LAFs, w, h):
+    """LAF.py:407-417."""
+    w, h = float(w), float(h)
+    return _scale(LAFs, min(h, w), w, h)
+
+
+def normalizeLAFs(LAFs, w, h):
+    """LAF.py:419-429 (coefficients rounded to float32 exactly as the reference's coef tensor)."""
+    w, h = float(w), float(h)
+    ms = np.float32(min(h, w))
+    return _scale(LAFs, float(np.float32(1.0) / ms), float(np.float32(1.0 / w)), float(np.float32(1.0 / h)))
+
+
+def get_pyramid_and_level_index_for_LAFs(dLAFs, plan, PS):
+    """LAF.py:453-472 (float64 argmin on device instead of scipy cdist on the host).  `plan` is the pyramid plan
+    of the detector (carries sigmas and pixel distances).  Returns int32 (octave, level) tensors."""
+    dLAFs = L.f32c(dLAFs, "dLAFs")
+    n = dLAFs.size(0)
+    o = torch.empty(n, dtype=torch.int32, device=dLAFs.device)
+    l = torch.empty(n, dtype=torch.int32, device=dLAFs.device)
+    L.check(L.lib().ag_pyramid_level_for_lafs(C.byref(plan), L.ptr(dLAFs), n, PS, L.ptr(o), L.ptr(l), L.stream_ptr()))
+    return o, l
+
+
+def get_LAFs_scales(LAFs):
+    return torch.sqrt(torch.abs(LAFs[:, 0, 0] * LAFs[:, 1, 1] - LAFs[:, 0, 1] * LAFs[:, 1, 0]) + 1e-12)
+
+
+def LAFs2ell(in_LAFs):
+    """LAF.py:225-240: [n,2,3] numpy LAFs -> [x y a b c] ellipse rows (float64 numpy, host-side output format)."""
+    LAFs = np.asarray(in_LAFs, dtype=np.float64).reshape(-1, 2, 3)
+    ell = np.zeros((len(LAFs), 5))
+    for i in range(len(LAFs)):
+        A = LAFs[i, :, :2]
+        scale = np.sqrt(A[0, 0] * A[1, 1] - A[0, 1] * A[1, 0] + 1e-10)
+        u, W, _ = np.linalg.svd(A / scale, full_matrices=True)
+        W = 1.0 / (W * W * scale * scale)
+        M = u @ np.diag(W) @ u.T
+        ell[i] = [LAFs[i, 0, 2], LAFs[i, 1, 2], M[0, 0], M[0, 1], M[1, 1]]
+    return ell

@@ -1,0 +1,555 @@
+// Hessian response, 3x3x3 NMS with sub-pixel soft-argmax, candidate compaction and global selection
+// (SURVEY.md §8a rows a3-a6).
+//
+// Replaces HessianResp.forward (HandCraftedModules.py:58-78), NMS3d / NMS3dAndComposeA
+// (HandCraftedModules.py:208-291) and the detection loop + global top-k of multiScaleDetector
+// (SparseImgRepresenter.py:53-111).  Response maps never touch HBM in the fused path: each CTA stages a
+// 36x36 window of three pyramid levels in shared memory, derives the three 34x34 response windows and
+// runs NMS, border/octave-map masking, counting, soft-argmax and compaction from there.
+//
+// Integer exactness: given identical inputs the set of surviving pixels is identical to the reference's
+// because every float op that decides survival is done in the reference's order with explicit
+// non-contracted intrinsics (__fmul_rn/__fsub_rn/__fadd_rn): the Hessian determinant, `(x - max) + 1e-5 > 0`,
+// `resp * (1 - octaveMap)` and the float->uint8 wrap of the octave map (Q4).
+#include "common.cuh"
+
+namespace ag {
+
+constexpr int DT = 32;            // output tile edge
+constexpr int DNT = 256;          // threads per CTA
+constexpr int RW = DT + 2;        // response window edge (tile + 1 halo)
+constexpr int PW = DT + 4;        // pyramid window edge (tile + 2 halo)
+constexpr int SEQ_PIX_BITS = 27;  // seq = slot << 27 | pixel
+
+struct DetectOctave {
+    const float* lvl[3];  // FROM_PYR: pyramid levels l-1,l,l+1 ([B,h,w]); else response maps low/cur/high
+    float s4[3];          // sigma^4 (python double -> float32), FROM_PYR only
+    float sc[3];          // scales as float32 (torch.FloatTensor(scales), Utils.py:133-135)
+    int h, w, tiles_x, tiles_y, tile_base;
+    int slot, prev_slot;  // level slot of this launch / of the previous detection level in the octave (-1: none)
+    const uint8_t* P_in;  // resolved octave map before the previous level (NULL = zeros)
+    const uint8_t* T_in;  // tentative map written by the previous level (valid iff that level had >1 positives)
+    uint8_t* P_out;       // resolved map before THIS level (for the next level's fallback)
+    uint8_t* T_out;       // tentative map after this level
+};
+
+struct DetectParams {
+    DetectOctave oct[AG_MAX_OCTAVES];
+    int n_oct, total_tiles;
+    float th;
+    int mr_border;
+    int cand_cap, n_slots;
+    float* cand_val;
+    uint32_t* cand_seq;
+    float* cand_scyx;
+    int* cand_count;
+    int* level_pos;
+    int* level_emit;
+};
+
+__device__ __forceinline__ float hessian_at(const float (*s)[PW + 1], int py, int px, float s4, float th) {
+    // (py,px) indexes the pyramid window; neighbours already hold replicate-clamped values.
+    const float c = s[py][px];
+    const float gxx = __fadd_rn(__fsub_rn(s[py][px - 1], __fmul_rn(2.0f, c)), s[py][px + 1]);
+    const float gyy = __fadd_rn(__fsub_rn(s[py - 1][px], __fmul_rn(2.0f, c)), s[py + 1][px]);
+    const float gxa = __fsub_rn(__fmul_rn(0.5f, s[py - 1][px - 1]), __fmul_rn(0.5f, s[py - 1][px + 1]));
+    const float gxb = __fsub_rn(__fmul_rn(0.5f, s[py + 1][px - 1]), __fmul_rn(0.5f, s[py + 1][px + 1]));
+    const float gxy = __fsub_rn(__fmul_rn(0.5f, gxa), __fmul_rn(0.5f, gxb));
+    const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));
+    const float r = __fmul_rn(fabsf(det), s4);
+    return fmaxf(__fsub_rn(r, th), 0.0f);  // torch.clamp(resp - th, min=0), SparseImgRepresenter.py:77
+}
+
+__device__ __forceinline__ uint8_t float_to_u8_wrap(float v) {
+    // torch-CPU float32 -> uint8: truncate toward zero, keep the low 8 bits (Q4).
+    if (!(fabsf(v) < 2147483648.0f)) return 0;
+    return (uint8_t)(__float2int_rz(v) & 0xFF);
+}
+
+template <bool FROM_PYR>
+__global__ void __launch_bounds__(DNT) detect_level_kernel(const DetectParams P) {
+    __shared__ float s_pyr[FROM_PYR ? 3 : 1][PW][PW + 1];
+    __shared__ float s_resp[3][RW][RW + 1];
+    __shared__ int s_cnt[3];  // pos, emit, base
+
+    // locate octave for this tile
+    int t = blockIdx.x, oi = 0;
+#pragma unroll 1
+    for (int i = 1; i < P.n_oct; i++)
+        if (t >= P.oct[i].tile_base) oi = i;
+    const DetectOctave& O = P.oct[oi];
+    t -= O.tile_base;
+    const int b = blockIdx.y;
+    const int h = O.h, w = O.w;
+    const int ty = t / O.tiles_x, tx = t - ty * O.tiles_x;
+    const int y0 = ty * DT, x0 = tx * DT;
+    const size_t img_off = (size_t)b * h * w;
+
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+
+    // ---- 1. response windows (origin y0-1, x0-1); zero outside the image (== conv zero padding) --------
+    if (FROM_PYR) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const float* src = O.lvl[d] + img_off;
+            for (int i = threadIdx.x; i < PW * PW; i += DNT) {
+                int ly = i / PW, lx = i - ly * PW;
+                int gy = clampi(y0 - 2 + ly, 0, h - 1), gx = clampi(x0 - 2 + lx, 0, w - 1);
+                s_pyr[FROM_PYR ? d : 0][ly][lx] = __ldg(src + (size_t)gy * w + gx);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            for (int i = threadIdx.x; i < RW * RW; i += DNT) {
+                int ly = i / RW, lx = i - ly * RW;
+                int gy = y0 - 1 + ly, gx = x0 - 1 + lx;
+                float r = 0.f;
+                if (gy >= 0 && gy < h && gx >= 0 && gx < w) r = hessian_at(s_pyr[FROM_PYR ? d : 0], ly + 1, lx + 1, O.s4[d], P.th);
+                s_resp[d][ly][lx] = r;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const float* src = O.lvl[d] + img_off;
+            for (int i = threadIdx.x; i < RW * RW; i += DNT) {
+                int ly = i / RW, lx = i - ly * RW;
+                int gy = y0 - 1 + ly, gx = x0 - 1 + lx;
+                s_resp[d][ly][lx] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? __ldg(src + (size_t)gy * w + gx) : 0.f;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 2. per-pixel NMS + masking --------------------------------------------------------------------
+    bool use_T = false;
+    if (O.prev_slot >= 0 && O.T_in != nullptr) use_T = P.level_pos[b * P.n_slots + O.prev_slot] > 1;
+    const uint8_t* om_src = use_T ? O.T_in : O.P_in;
+    const bool border_ok = (P.mr_border < w) && (P.mr_border < h);  // Utils.py:141
+
+    constexpr int PPT = DT * DT / DNT;  // 4 pixels per thread
+    float vals[PPT];
+    int n_pos = 0, n_emit = 0;
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        const int i = threadIdx.x + k * DNT;
+        const int ly = i / DT, lx = i - ly * DT;
+        const int gy = y0 + ly, gx = x0 + lx;
+        float val = 0.f;
+        if (gy < h && gx < w) {
+            const float x = s_resp[1][ly + 1][lx + 1];
+            float m = x;
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+#pragma unroll
+                for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; dx++) {
+                        const int ny = gy + dy, nx = gx + dx;
+                        if (ny >= 0 && ny < h && nx >= 0 && nx < w) m = fmaxf(m, s_resp[d][ly + 1 + dy][lx + 1 + dx]);
+                    }
+            // NMS3d: ((x - m + eps) > 0) * x      HandCraftedModules.py:220
+            float nms = (__fadd_rn(__fsub_rn(x, m), 1e-5f) > 0.f) ? x : 0.f;
+            // zero_response_at_border(int(mrSize))   Utils.py:140-148
+            if (!border_ok || gy < P.mr_border || gy >= h - P.mr_border || gx < P.mr_border || gx >= w - P.mr_border) nms = 0.f;
+            const size_t p = img_off + (size_t)gy * w + gx;
+            const uint8_t om = om_src ? om_src[p] : (uint8_t)0;
+            val = __fmul_rn(nms, __fsub_rn(1.0f, (float)om));  // * (1 - octaveMap.float())   :246
+            if (O.P_out) O.P_out[p] = om;
+            if (O.T_out) O.T_out[p] = float_to_u8_wrap(__fadd_rn((float)om, val));  // (octaveMap.float()+resp).byte()  :256
+            n_pos += (val > 0.f);
+            n_emit += (val != 0.f);
+        }
+        vals[k] = val;
+    }
+
+    // ---- 3. counts and slot allocation -------------------------------------------------------------------
+    const unsigned lane = threadIdx.x & 31;
+    int wp = n_pos, we = n_emit;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wp += __shfl_xor_sync(0xffffffffu, wp, o);
+        we += __shfl_xor_sync(0xffffffffu, we, o);
+    }
+    // exclusive prefix of n_emit within the warp
+    int incl = n_emit;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+    }
+    int warp_base = 0;
+    if (lane == 0 && we > 0) {
+        atomicAdd(&s_cnt[0], wp);
+        warp_base = atomicAdd(&s_cnt[1], we);
+    }
+    warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt[1] > 0) {
+        atomicAdd(&P.level_pos[b * P.n_slots + O.slot], s_cnt[0]);
+        atomicAdd(&P.level_emit[b * P.n_slots + O.slot], s_cnt[1]);
+        s_cnt[2] = atomicAdd(&P.cand_count[b], s_cnt[1]);
+    }
+    __syncthreads();
+    if (n_emit == 0) return;
+    int dst = s_cnt[2] + warp_base + (incl - n_emit);
+
+    // ---- 4. soft-argmax + emission   HandCraftedModules.py:266-290 ------------------------------------
+    const float min_size = (float)min(h, w);
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        if (vals[k] == 0.f) continue;
+        const int i = threadIdx.x + k * DNT;
+        const int ly = i / DT, lx = i - ly * DT;
+        const int gy = y0 + ly, gx = x0 + lx;
+        if (dst < P.cand_cap) {
+            float ns = 0.f, ny = 0.f, nx = 0.f, den = 0.f;
+#pragma unroll
+            for (int d = 0; d < 3; d++)
+#pragma unroll
+                for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++) {
+                        const float r = s_resp[d][ly + dy][lx + dx];
+                        ns = fmaf(O.sc[d], r, ns);
+                        ny = fmaf(-0.5f + (float)dy, r, ny);  // offsets [-0.5, 0.5, 1.5]  (Q2)
+                        nx = fmaf(-0.5f + (float)dx, r, nx);
+                        den += r;
+                    }
+            den = __fadd_rn(den, 1e-8f);
+            const float sc = __fdiv_rn(__fdiv_rn(ns, den), min_size);
+            const float yy = __fdiv_rn(__fadd_rn(__fdiv_rn(ny, den), (float)gy), (float)h);
+            const float xx = __fdiv_rn(__fadd_rn(__fdiv_rn(nx, den), (float)gx), (float)w);
+            const size_t o = (size_t)b * P.cand_cap + dst;
+            P.cand_val[o] = vals[k];
+            P.cand_seq[o] = ((uint32_t)O.slot << SEQ_PIX_BITS) | (uint32_t)(gy * w + gx);
+            P.cand_scyx[o * 3 + 0] = sc;
+            P.cand_scyx[o * 3 + 1] = yy;
+            P.cand_scyx[o * 3 + 2] = xx;
+        }
+        dst++;
+    }
+}
+
+// ---- standalone Hessian response map (HessianResp module API + parity tests) -------------------------
+__global__ void hessian_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w, float s4, float th) {
+    __shared__ float s[PW][PW + 1];  // uses the (DT+2)^2 corner of the window
+    const int b = blockIdx.z, y0 = blockIdx.y * DT, x0 = blockIdx.x * DT;
+    const float* src = in + (size_t)b * h * w;
+    for (int i = threadIdx.x; i < RW * RW; i += DNT) {
+        int ly = i / RW, lx = i - ly * RW;
+        int gy = clampi(y0 - 1 + ly, 0, h - 1), gx = clampi(x0 - 1 + lx, 0, w - 1);
+        s[ly][lx] = __ldg(src + (size_t)gy * w + gx);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < DT * DT; i += DNT) {
+        int ly = i / DT, lx = i - ly * DT;
+        int gy = y0 + ly, gx = x0 + lx;
+        if (gy < h && gx < w) out[(size_t)b * h * w + (size_t)gy * w + gx] = hessian_at(s, ly + 1, lx + 1, s4, th);
+    }
+}
+
+// ---- global selection ---------------------------------------------------------------------------------
+constexpr int SNT = 1024;
+
+struct SelectParams {
+    const float* cand_val;
+    const uint32_t* cand_seq;
+    const float* cand_scyx;
+    const int* cand_count;
+    const int* level_pos;
+    const int* level_emit;
+    int cand_cap, n_slots, n_det;  // n_det = detection levels per octave
+    int num_features, out_cap, sort_cap;  // sort_cap: power of two >= max selectable
+    float a_scale;
+    float* resp;
+    float* lafs;
+    int* oct;
+    int* lvl;
+    int* count;
+};
+
+__global__ void __launch_bounds__(SNT) select_kernel(const SelectParams P) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);
+    int* s_idx = reinterpret_cast<int*>(smem_raw + sizeof(unsigned long long) * P.sort_cap);
+    __shared__ int s_hist[256];
+    __shared__ unsigned s_accept;  // bit per slot
+    __shared__ int s_misc[4];      // 0: sorted mode, 1: m (number to select), 2: digit, 3: fill counter
+    __shared__ unsigned long long s_prefix;
+
+    const int b = blockIdx.x;
+    const int n = min(P.cand_count[b], P.cand_cap);
+    const float* val = P.cand_val + (size_t)b * P.cand_cap;
+    const uint32_t* seq = P.cand_seq + (size_t)b * P.cand_cap;
+    const int nf = P.num_features;
+
+    if (threadIdx.x == 0) {
+        unsigned acc = 0;
+        long long total = 0;
+        bool trimmed = false;
+        for (int s = 0; s < P.n_slots; s++) {
+            const int pos = P.level_pos[b * P.n_slots + s], emit = P.level_emit[b * P.n_slots + s];
+            if (pos > 1) {  // HandCraftedModules.py:253
+                acc |= 1u << s;
+                if (nf > 0 && nf < pos) { total += nf; trimmed = true; }  // per-level topk :259
+                else total += emit;
+            }
+        }
+        s_accept = acc;
+        const bool sorted = (nf > 0) && (total > nf || trimmed);  // SparseImgRepresenter.py:104
+        long long m = sorted ? nf : total;
+        if (m > P.out_cap) m = P.out_cap;
+        if (m > n) m = n;
+        s_misc[0] = sorted;
+        s_misc[1] = (int)m;
+        s_misc[3] = 0;
+        s_prefix = 0ull;
+    }
+    __syncthreads();
+    const unsigned accept = s_accept;
+    const bool sorted = s_misc[0] != 0;
+    const int m = s_misc[1];
+
+    auto key_of = [&](int i) -> unsigned long long {
+        const uint32_t sq = seq[i];
+        if (!((accept >> (sq >> SEQ_PIX_BITS)) & 1u)) return 0ull;
+        const unsigned long long lo = (unsigned long long)(0xFFFFFFFFu - sq);
+        // +1 keeps every valid key above the invalid key 0
+        return sorted ? (((unsigned long long)float_to_ordered(val[i]) << 32) | lo) : (lo + 1ull);
+    };
+
+    if (m > 0) {
+        // radix select of the m-th largest key, 8 bits per pass from the top
+        int remaining = m;
+        for (int pass = 7; pass >= 0; pass--) {
+            for (int i = threadIdx.x; i < 256; i += SNT) s_hist[i] = 0;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            const int shift = pass * 8;
+            const unsigned long long hi_mask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
+            for (int i = threadIdx.x; i < n; i += SNT) {
+                const unsigned long long k = key_of(i);
+                if ((k & hi_mask) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & 0xFF)], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int cum = 0, d = 255;
+                for (; d > 0; d--) {
+                    if (cum + s_hist[d] >= remaining) break;
+                    cum += s_hist[d];
+                }
+                s_misc[2] = remaining - cum;  // still needed inside digit d
+                s_prefix = prefix | ((unsigned long long)d << shift);
+            }
+            __syncthreads();
+            remaining = s_misc[2];
+        }
+        const unsigned long long kth = s_prefix;  // keys are unique (seq unique) => exactly m keys >= kth
+        for (int i = threadIdx.x; i < P.sort_cap; i += SNT) { s_key[i] = 0ull; s_idx[i] = -1; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += SNT) {
+            const unsigned long long k = key_of(i);
+            if (k >= kth && k != 0ull) {
+                const int pos = atomicAdd(&s_misc[3], 1);
+                if (pos < P.sort_cap) { s_key[pos] = k; s_idx[pos] = i; }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && s_misc[3] < s_misc[1]) s_misc[1] = s_misc[3];  // candidate list overflowed
+        // bitonic sort, descending by key
+        for (int k2 = 2; k2 <= P.sort_cap; k2 <<= 1) {
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < P.sort_cap; i += SNT) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long a = s_key[i], c = s_key[ixj];
+                        const bool desc = (i & k2) == 0;
+                        if (desc ? (a < c) : (a > c)) {
+                            s_key[i] = c; s_key[ixj] = a;
+                            const int t = s_idx[i]; s_idx[i] = s_idx[ixj]; s_idx[ixj] = t;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    // outputs
+    __syncthreads();
+    const int m_out = s_misc[1];
+    const float* scyx = P.cand_scyx + (size_t)b * P.cand_cap * 3;
+    for (int i = threadIdx.x; i < m_out; i += SNT) {
+        const int c = s_idx[i];
+        const size_t o = (size_t)b * P.out_cap + i;
+        const float sc = __fmul_rn(P.a_scale, scyx[c * 3 + 0]);  // mrSize * LAFs[:, :, 0:2]   SparseImgRepresenter.py:198
+        P.resp[o] = val[c];
+        float* L = P.lafs + o * 6;
+        L[0] = sc; L[1] = 0.f; L[2] = scyx[c * 3 + 2];
+        L[3] = 0.f; L[4] = sc; L[5] = scyx[c * 3 + 1];
+        const int slot = (int)(seq[c] >> SEQ_PIX_BITS);
+        P.oct[o] = slot / P.n_det;
+        P.lvl[o] = slot % P.n_det;  // detection level_idx - 1: patches come from the level below (:94)
+    }
+    if (threadIdx.x == 0) P.count[b] = m_out;
+}
+
+}  // namespace ag
+
+using namespace ag;
+
+extern "C" {
+
+size_t ag_detect_ws_bytes(const ag_pyramid_plan_t* p, int cand_cap) {
+    if (!p || cand_cap <= 0) return 0;
+    const size_t B = p->B, slots = (size_t)p->n_octaves * (p->n_levels - 2);
+    size_t n = 0;
+    n += align_up(B * cand_cap * sizeof(float), 256);
+    n += align_up(B * cand_cap * sizeof(uint32_t), 256);
+    n += align_up(B * cand_cap * 3 * sizeof(float), 256);
+    n += align_up((B + 2 * B * slots) * sizeof(int), 256);
+    size_t px = 0;
+    for (int o = 0; o < p->n_octaves; o++) px += (size_t)p->h[o] * p->w[o];
+    n += align_up(4 * B * px, 256);
+    return n;
+}
+
+int ag_detect_ws_carve(const ag_pyramid_plan_t* p, int cand_cap, void* d_ws, ag_detect_ws_t* ws) {
+    AG_REQUIRE(p && d_ws && ws && cand_cap > 0, "bad arguments");
+    const size_t B = p->B, slots = (size_t)p->n_octaves * (p->n_levels - 2);
+    AG_REQUIRE(slots <= 32, "too many detection levels (max 32 slots)");
+    AG_REQUIRE((long long)p->H * p->W < (1ll << SEQ_PIX_BITS), "image too large for the candidate key");
+    unsigned char* c = (unsigned char*)d_ws;
+    ws->B = p->B; ws->cand_cap = cand_cap; ws->n_level_slots = (int)slots;
+    ws->d_cand_val = (float*)c; c += align_up(B * cand_cap * sizeof(float), 256);
+    ws->d_cand_seq = (uint32_t*)c; c += align_up(B * cand_cap * sizeof(uint32_t), 256);
+    ws->d_cand_scyx = (float*)c; c += align_up(B * cand_cap * 3 * sizeof(float), 256);
+    ws->d_cand_count = (int*)c;
+    ws->d_level_pos = ws->d_cand_count + B;
+    ws->d_level_emit = ws->d_level_pos + B * slots;
+    c += align_up((B + 2 * B * slots) * sizeof(int), 256);
+    ws->d_octave_maps = c;
+    return AG_OK;
+}
+
+static int fill_common(DetectParams& P, const ag_detect_ws_t* ws, float th, int mr_border) {
+    P.th = th; P.mr_border = mr_border;
+    P.cand_cap = ws->cand_cap; P.n_slots = ws->n_level_slots;
+    P.cand_val = ws->d_cand_val; P.cand_seq = ws->d_cand_seq; P.cand_scyx = ws->d_cand_scyx;
+    P.cand_count = ws->d_cand_count; P.level_pos = ws->d_level_pos; P.level_emit = ws->d_level_emit;
+    return AG_OK;
+}
+
+int ag_detect(const ag_pyramid_plan_t* p, const float* d_pyr, float th, int mr_border, ag_detect_ws_t* ws, void* stream) {
+    AG_REQUIRE(p && d_pyr && ws, "NULL argument");
+    AG_REQUIRE(ws->B == p->B, "workspace batch mismatch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_det = p->n_levels - 2;
+    AG_REQUIRE(ws->n_level_slots == p->n_octaves * n_det, "workspace slot mismatch");
+    const size_t B = p->B;
+    int rc = check_cuda(cudaMemsetAsync(ws->d_cand_count, 0, (B + 2 * B * ws->n_level_slots) * sizeof(int), st), "memset counters");
+    if (rc != AG_OK) return rc;
+    // octave-map scratch: every octave owns 4 uint8 maps [B,h,w] (resolved P and tentative T, ping-ponged),
+    // packed octave after octave: 4 * sum_o B*h_o*w_o bytes in total.
+    for (int k = 0; k < n_det; k++) {
+        DetectParams P;
+        memset(&P, 0, sizeof(P));
+        fill_common(P, ws, th, mr_border);
+        P.n_oct = p->n_octaves;
+        int tiles = 0;
+        size_t oct_off = 0;
+        for (int o = 0; o < p->n_octaves; o++) {
+            DetectOctave& O = P.oct[o];
+            const int l = k + 1;
+            for (int d = 0; d < 3; d++) {
+                O.lvl[d] = d_pyr + p->level_offset[o][l - 1 + d];
+                const double s = p->sigma[o][l - 1 + d];
+                O.s4[d] = (float)pow(s, 4.0);  // python `scale**4` (double pow), cast to float32 by torch's scalar mul
+                O.sc[d] = (float)s;
+            }
+            O.h = p->h[o]; O.w = p->w[o];
+            O.tiles_x = cdiv(O.w, DT); O.tiles_y = cdiv(O.h, DT);
+            O.tile_base = tiles;
+            tiles += O.tiles_x * O.tiles_y;
+            O.slot = o * n_det + k;
+            O.prev_slot = (k > 0) ? O.slot - 1 : -1;
+            uint8_t* base = ws->d_octave_maps;
+            const size_t osz = B * (size_t)O.h * O.w;
+            uint8_t* r = base + 4 * oct_off;
+            uint8_t* Pbuf[2] = {r, r + osz};
+            uint8_t* Tbuf[2] = {r + 2 * osz, r + 3 * osz};
+            O.P_in = (k >= 2) ? Pbuf[(k - 1) & 1] : nullptr;   // resolved map before level k-1 (zeros for k-1 == 0)
+            O.T_in = (k >= 1) ? Tbuf[(k - 1) & 1] : nullptr;   // tentative map after level k-1
+            O.P_out = (k >= 1 && k + 1 < n_det) ? Pbuf[k & 1] : nullptr;
+            O.T_out = (k + 1 < n_det) ? Tbuf[k & 1] : nullptr;
+            oct_off += osz;
+        }
+        P.total_tiles = tiles;
+        dim3 grid(tiles, p->B);
+        detect_level_kernel<true><<<grid, DNT, 0, st>>>(P);
+        AG_CHECK_LAUNCH("detect_level_kernel");
+    }
+    return AG_OK;
+}
+
+int ag_detect_level_from_responses(const float* d_low, const float* d_cur, const float* d_high, int h, int w,
+                                   const double scales[3], int mr_border, const uint8_t* d_omap_in, uint8_t* d_omap_out,
+                                   int slot, ag_detect_ws_t* ws, void* stream) {
+    AG_REQUIRE(d_low && d_cur && d_high && ws && scales, "NULL argument");
+    AG_REQUIRE(ws->B == 1, "single-image entry point");
+    AG_REQUIRE(slot >= 0 && slot < ws->n_level_slots, "slot out of range");
+    DetectParams P;
+    memset(&P, 0, sizeof(P));
+    fill_common(P, ws, 0.f, mr_border);
+    P.n_oct = 1;
+    DetectOctave& O = P.oct[0];
+    O.lvl[0] = d_low; O.lvl[1] = d_cur; O.lvl[2] = d_high;
+    for (int d = 0; d < 3; d++) { O.sc[d] = (float)scales[d]; O.s4[d] = 1.f; }
+    O.h = h; O.w = w; O.tiles_x = cdiv(w, DT); O.tiles_y = cdiv(h, DT); O.tile_base = 0;
+    O.slot = slot; O.prev_slot = -1;
+    O.P_in = d_omap_in; O.T_in = nullptr; O.P_out = nullptr; O.T_out = d_omap_out;
+    P.total_tiles = O.tiles_x * O.tiles_y;
+    detect_level_kernel<false><<<dim3(P.total_tiles, 1), DNT, 0, (cudaStream_t)stream>>>(P);
+    AG_CHECK_LAUNCH("detect_level_kernel<resp>");
+    return AG_OK;
+}
+
+int ag_hessian_response(const float* d_in, float* d_out, int B, int h, int w, double sigma, float th, void* stream) {
+    AG_REQUIRE(d_in && d_out && B >= 1 && h >= 1 && w >= 1, "bad arguments");
+    dim3 grid(cdiv(w, DT), cdiv(h, DT), B);
+    hessian_kernel<<<grid, DNT, 0, (cudaStream_t)stream>>>(d_in, d_out, h, w, (float)pow(sigma, 4.0), th);
+    AG_CHECK_LAUNCH("hessian_kernel");
+    return AG_OK;
+}
+
+int ag_select_keypoints(const ag_pyramid_plan_t* p, const ag_detect_ws_t* ws, int num_features, float a_scale, int out_cap,
+                        float* d_resp, float* d_lafs, int* d_oct, int* d_lvl, int* d_count, void* stream) {
+    AG_REQUIRE(p && ws && d_resp && d_lafs && d_oct && d_lvl && d_count, "NULL argument");
+    AG_REQUIRE(out_cap >= 1, "out_cap must be positive");
+    const int need = (num_features > 0) ? (num_features < out_cap ? num_features : out_cap) : out_cap;
+    int sort_cap = 32;
+    while (sort_cap < need) sort_cap <<= 1;
+    const size_t smem = (size_t)sort_cap * (sizeof(unsigned long long) + sizeof(int));
+    if (smem > 200 * 1024) {
+        set_error("ag_select_keypoints: selecting %d keypoints needs %zu B of shared memory (max 200 KiB)", need, smem);
+        return AG_ERR_CAPACITY;
+    }
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        int rc = check_cuda(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "select smem attr");
+        if (rc != AG_OK) return rc;
+        configured = smem;
+    }
+    SelectParams S;
+    S.cand_val = ws->d_cand_val; S.cand_seq = ws->d_cand_seq; S.cand_scyx = ws->d_cand_scyx;
+    S.cand_count = ws->d_cand_count; S.level_pos = ws->d_level_pos; S.level_emit = ws->d_level_emit;
+    S.cand_cap = ws->cand_cap; S.n_slots = ws->n_level_slots; S.n_det = p->n_levels - 2;
+    S.num_features = num_features; S.out_cap = out_cap; S.sort_cap = sort_cap; S.a_scale = a_scale;
+    S.resp = d_resp; S.lafs = d_lafs; S.oct = d_oct; S.lvl = d_lvl; S.count = d_count;
+    select_kernel<<<ws->B, SNT, smem, (cudaStream_t)stream>>>(S);
+    AG_CHECK_LAUNCH("select_kernel");
+    return AG_OK;
+}
+
+}  // extern "C"

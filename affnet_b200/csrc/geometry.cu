@@ -1,0 +1,194 @@
+// Per-keypoint geometry: affine-shape filter, orientation compose, LAF (de)normalisation
+// (SURVEY.md §8a rows a10 (partly), a11, a13, a14).
+//
+// Replaces the tail of getAffineShape (SparseImgRepresenter.py:136-162) with batch_eig2x2 (Utils.py:168-175)
+// and checkTouchBoundary (LAF.py:98-104), the compose step of getOrientation (SparseImgRepresenter.py:175)
+// and denormalizeLAFs / normalizeLAFs (LAF.py:407-429).
+// Decisions (eigen-ratio test, boundary test) use the reference's fp32 operation order with non-contracted
+// intrinsics so that identical A matrices give the identical survivor set.
+#include "common.cuh"
+
+namespace ag {
+
+constexpr int GNT = 1024;
+
+struct ShapeParams {
+    const float* A;      // [B,cap,2,2]
+    const float* resp;   // [B,cap]
+    const float* lafs;   // [B,cap,2,3]
+    const int* oct;
+    const int* lvl;
+    const int* count_in;
+    int cap, num_features, out_cap, sort_cap;
+    float* resp_out;
+    float* lafs_out;
+    int* oct_out;
+    int* lvl_out;
+    int* count_out;
+};
+
+__device__ __forceinline__ bool shape_ok(const float* A, const float* NL) {
+    // batch_eig2x2 (Utils.py:168-175)
+    const float trace = __fadd_rn(A[0], A[3]);
+    const float det = __fsub_rn(__fmul_rn(A[0], A[3]), __fmul_rn(A[2], A[1]));
+    const float delta1 = __fsub_rn(__fmul_rn(trace, trace), __fmul_rn(4.0f, det));
+    float l1, l2;
+    if (delta1 > 0.f) {
+        const float delta = __fsqrt_rn(fabsf(delta1));
+        l1 = __fdiv_rn(__fadd_rn(trace, delta), 2.0f);
+        l2 = __fdiv_rn(__fsub_rn(trace, delta), 2.0f);
+    } else {
+        l1 = 1000.0f; l2 = 0.0001f;
+    }
+    const float ratio = fabsf(__fdiv_rn(l1, __fadd_rn(l2, 1e-8f)));
+    bool ok = (ratio < 6.0f) && (ratio > (float)(1.0 / 6.0));  // SparseImgRepresenter.py:149
+    // checkTouchBoundary (LAF.py:98-104): corners (+-1,+-1) through the normalised LAF must lie in [0,1] (Q5)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const float x = (c & 2) ? 1.f : -1.f, y = (c & 1) ? 1.f : -1.f;
+        const float ox = fmaf(NL[0], x, fmaf(NL[1], y, NL[2]));
+        const float oy = fmaf(NL[3], x, fmaf(NL[4], y, NL[5]));
+        ok = ok && !(ox > 1.0f || ox < 0.0f || oy > 1.0f || oy < 0.0f);
+    }
+    return ok;
+}
+
+__device__ __forceinline__ void compose_laf(const float* A, const float* L, float* NL) {
+    // new_LAF = [bmm(A, LAF[:, :, 0:2]), LAF[:, :, 2:]]   SparseImgRepresenter.py:138
+    NL[0] = fmaf(A[0], L[0], A[1] * L[3]); NL[1] = fmaf(A[0], L[1], A[1] * L[4]); NL[2] = L[2];
+    NL[3] = fmaf(A[2], L[0], A[3] * L[3]); NL[4] = fmaf(A[2], L[1], A[3] * L[4]); NL[5] = L[5];
+}
+
+__global__ void __launch_bounds__(GNT) shape_filter_kernel(const ShapeParams P) {
+    extern __shared__ unsigned long long s_key[];
+    __shared__ int s_surv;
+    const int b = blockIdx.x;
+    const int n = min(P.count_in[b], P.cap);
+    const float* A = P.A + (size_t)b * P.cap * 4;
+    const float* L = P.lafs + (size_t)b * P.cap * 6;
+    const float* R = P.resp + (size_t)b * P.cap;
+    if (threadIdx.x == 0) s_surv = 0;
+    __syncthreads();
+    // pass 1: count survivors
+    int local = 0;
+    for (int i = threadIdx.x; i < n; i += GNT) {
+        float NL[6];
+        compose_laf(A + i * 4, L + i * 6, NL);
+        local += shape_ok(A + i * 4, NL) ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_surv, local);
+    __syncthreads();
+    const int S = s_surv;
+    const bool sorted = (P.num_features > 0) && (S > P.num_features);  // SparseImgRepresenter.py:151
+    int m = sorted ? P.num_features : S;
+    if (m > P.out_cap) m = P.out_cap;
+    // pass 2: keys
+    for (int i = threadIdx.x; i < P.sort_cap; i += GNT) {
+        unsigned long long k = 0ull;
+        if (i < n) {
+            float NL[6];
+            compose_laf(A + i * 4, L + i * 6, NL);
+            const bool ok = shape_ok(A + i * 4, NL);
+            const unsigned hi = sorted ? float_to_ordered(ok ? R[i] : 0.f) : (ok ? 1u : 0u);
+            k = ((unsigned long long)hi << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+        }
+        s_key[i] = k;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= P.sort_cap; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P.sort_cap; i += GNT) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = s_key[i], c = s_key[ixj];
+                    const bool desc = (i & k2) == 0;
+                    if (desc ? (a < c) : (a > c)) { s_key[i] = c; s_key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int r = threadIdx.x; r < m; r += GNT) {
+        const int i = (int)(0xFFFFFFFFu - (unsigned)(s_key[r] & 0xFFFFFFFFull));
+        const size_t o = (size_t)b * P.out_cap + r;
+        float NL[6];
+        compose_laf(A + i * 4, L + i * 6, NL);
+        P.resp_out[o] = R[i];
+#pragma unroll
+        for (int q = 0; q < 6; q++) P.lafs_out[o * 6 + q] = NL[q];
+        P.oct_out[o] = P.oct[(size_t)b * P.cap + i];
+        P.lvl_out[o] = P.lvl[(size_t)b * P.cap + i];
+    }
+    if (threadIdx.x == 0) P.count_out[b] = m;
+}
+
+__global__ void lafs_rotate_kernel(float* __restrict__ lafs, const float* __restrict__ R, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float* L = lafs + (size_t)i * 6;
+    const float* r = R + (size_t)i * 4;
+    const float l00 = L[0], l01 = L[1], l10 = L[3], l11 = L[4];
+    L[0] = fmaf(l00, r[0], l01 * r[2]); L[1] = fmaf(l00, r[1], l01 * r[3]);
+    L[3] = fmaf(l10, r[0], l11 * r[2]); L[4] = fmaf(l10, r[1], l11 * r[3]);
+}
+
+__global__ void lafs_scale_kernel(const float* __restrict__ in, float* __restrict__ out, int n, float ac, float xc, float yc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* L = in + (size_t)i * 6;
+    float* O = out + (size_t)i * 6;
+    O[0] = __fmul_rn(L[0], ac); O[1] = __fmul_rn(L[1], ac); O[2] = __fmul_rn(L[2], xc);
+    O[3] = __fmul_rn(L[3], ac); O[4] = __fmul_rn(L[4], ac); O[5] = __fmul_rn(L[5], yc);
+}
+
+}  // namespace ag
+
+using namespace ag;
+
+extern "C" {
+
+int ag_affine_shape_filter(const float* d_A, const float* d_resp, const float* d_lafs, const int* d_oct, const int* d_lvl,
+                           const int* d_count_in, int B, int cap, int num_features, int out_cap, float* d_resp_out,
+                           float* d_lafs_out, int* d_oct_out, int* d_lvl_out, int* d_count_out, void* stream) {
+    AG_REQUIRE(d_A && d_resp && d_lafs && d_oct && d_lvl && d_count_in && d_resp_out && d_lafs_out && d_oct_out &&
+                   d_lvl_out && d_count_out, "NULL argument");
+    AG_REQUIRE(B >= 1 && cap >= 1 && out_cap >= 1, "bad sizes");
+    int sort_cap = 32;
+    while (sort_cap < cap) sort_cap <<= 1;
+    const size_t smem = (size_t)sort_cap * sizeof(unsigned long long);
+    if (smem > 200 * 1024) {
+        set_error("ag_affine_shape_filter: cap %d needs %zu B of shared memory (max 200 KiB)", cap, smem);
+        return AG_ERR_CAPACITY;
+    }
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        int rc = check_cuda(cudaFuncSetAttribute(shape_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "shape smem attr");
+        if (rc != AG_OK) return rc;
+        configured = smem;
+    }
+    ShapeParams P;
+    P.A = d_A; P.resp = d_resp; P.lafs = d_lafs; P.oct = d_oct; P.lvl = d_lvl; P.count_in = d_count_in;
+    P.cap = cap; P.num_features = num_features; P.out_cap = out_cap; P.sort_cap = sort_cap;
+    P.resp_out = d_resp_out; P.lafs_out = d_lafs_out; P.oct_out = d_oct_out; P.lvl_out = d_lvl_out; P.count_out = d_count_out;
+    shape_filter_kernel<<<B, GNT, smem, (cudaStream_t)stream>>>(P);
+    AG_CHECK_LAUNCH("shape_filter_kernel");
+    return AG_OK;
+}
+
+int ag_lafs_apply_rotation(float* d_lafs, const float* d_R, int n, void* stream) {
+    AG_REQUIRE(d_lafs && d_R, "NULL argument");
+    if (n <= 0) return AG_OK;
+    lafs_rotate_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d_lafs, d_R, n);
+    AG_CHECK_LAUNCH("lafs_rotate_kernel");
+    return AG_OK;
+}
+
+int ag_lafs_scale(const float* d_in, float* d_out, int n, float a_coef, float x_coef, float y_coef, void* stream) {
+    AG_REQUIRE(d_in && d_out, "NULL argument");
+    if (n <= 0) return AG_OK;
+    lafs_scale_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, n, a_coef, x_coef, y_coef);
+    AG_CHECK_LAUNCH("lafs_scale_kernel");
+    return AG_OK;
+}
+
+}  // extern "C"

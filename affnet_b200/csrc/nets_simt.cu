@@ -1,0 +1,470 @@
+// AffNet / OriNet / HardNet forward, fp32 SIMT path.
+//
+// Replaces AffNetFast.forward (architectures.py:204-252), OriNetFast.forward (architectures.py:33-82) and
+// HardNet.forward (HardNet.py:61-101) in eval mode: per-patch input normalisation, six conv3x3 + BatchNorm
+// (affine=False, eps 1e-5, running stats; folded into the weights at upload) + ReLU, then the 8x8 head.
+// This is the exact-fp32 engine: every layer is a direct convolution with the whole (padded) input of one
+// patch staged in shared memory, activations in NCHW through L2-resident scratch.  The tensor-core engine
+// (nets_tc.cu) replaces the inner layers where present; first layer (K=9) and heads stay here.
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace ag {
+
+constexpr float BN_EPS = 1e-5f;
+constexpr int CNT = 256;
+
+struct LayerCfg {
+    int cin, cout, stride, hin;
+};
+static const LayerCfg kAffCfg[6] = {{1, 16, 1, 32}, {16, 16, 1, 32}, {16, 32, 2, 32}, {32, 32, 1, 16}, {32, 64, 2, 16}, {64, 64, 1, 8}};
+static const LayerCfg kHardCfg[6] = {{1, 32, 1, 32}, {32, 32, 1, 32}, {32, 64, 2, 32}, {64, 64, 1, 16}, {64, 128, 2, 16}, {128, 128, 1, 8}};
+
+}  // namespace ag
+
+struct ag_net {
+    int kind;
+    float* d_w[6];     // [9][cin][cout], BN folded
+    float* d_b[6];     // [cout]
+    float* d_head_w;   // AffNet [3][4096], OriNet [2][4096], HardNet [8192][128]
+    float* d_head_b;   // AffNet bias[3], OriNet bias[2], HardNet {scale[128], shift[128]}
+    float* d_all;      // single allocation backing everything
+};
+
+namespace ag {
+
+// ---- direct 3x3 convolution, one patch (x cout tile) per CTA -------------------------------------------
+template <int CIN, int COUT, int HIN, int STRIDE, int CT, int CK, bool NORM>
+__global__ void __launch_bounds__(CNT) conv3x3_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                       const float* __restrict__ wpk, const float* __restrict__ bias,
+                                                       int group, const int* __restrict__ count) {
+    constexpr int HOUT = HIN / STRIDE, NP = HOUT * HOUT, PPT = 4, PT = NP / PPT, CGN = CNT / PT, CPT = CT / CGN;
+    constexpr int HP = HIN + 2, WP = HIN + 2;
+    static_assert(PT * CGN == CNT && CPT * CGN == CT && CPT % 4 == 0, "bad tiling");
+    static_assert(CIN % CK == 0, "bad cin chunk");
+    extern __shared__ float smem[];
+    float* s_in = smem;                    // [CIN][HP][WP]
+    float* s_w = smem + CIN * HP * WP;     // [9][CK][CT]
+    __shared__ float s_red[CNT / 32][2];
+
+    const int pi = blockIdx.x;
+    if (count != nullptr && (pi % group) >= count[pi / group]) return;
+    const int ct0 = blockIdx.y * CT;
+    const float* src = in + (size_t)pi * CIN * HIN * HIN;
+
+    float mean = 0.f, inv = 1.f;
+    if (NORM) {
+        // input_norm: (x - mean) / (std_unbiased + 1e-7)    architectures.py:231-235, HardNet.py:92-96
+        float s = 0.f;
+        for (int i = threadIdx.x; i < HIN * HIN; i += CNT) s += src[i];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][0] = s;
+        __syncthreads();
+        s = 0.f;
+        for (int i = 0; i < CNT / 32; i++) s += s_red[i][0];
+        mean = s / (float)(HIN * HIN);
+        float q = 0.f;
+        for (int i = threadIdx.x; i < HIN * HIN; i += CNT) { const float d = src[i] - mean; q = fmaf(d, d, q); }
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][1] = q;
+        __syncthreads();
+        q = 0.f;
+        for (int i = 0; i < CNT / 32; i++) q += s_red[i][1];
+        inv = 1.f / (sqrtf(q / (float)(HIN * HIN - 1)) + 1e-7f);
+    }
+    // stage the zero-padded input
+    for (int i = threadIdx.x; i < CIN * HP * WP; i += CNT) {
+        const int c = i / (HP * WP), r = i - c * HP * WP, y = r / WP, x = r - y * WP;
+        float v = 0.f;
+        if (y >= 1 && y <= HIN && x >= 1 && x <= HIN) {
+            v = src[(size_t)c * HIN * HIN + (y - 1) * HIN + (x - 1)];
+            if (NORM) v = (v - mean) * inv;
+        }
+        s_in[i] = v;
+    }
+
+    const int pt = threadIdx.x % PT, cg = threadIdx.x / PT;
+    int poff[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        const int p = pt + k * PT, y = p / HOUT, x = p - y * HOUT;
+        poff[k] = (y * STRIDE) * WP + x * STRIDE;
+    }
+    float acc[PPT][CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; j++) {
+        const float bv = bias[ct0 + cg * CPT + j];
+#pragma unroll
+        for (int k = 0; k < PPT; k++) acc[k][j] = bv;
+    }
+
+    for (int c0 = 0; c0 < CIN; c0 += CK) {
+        __syncthreads();  // previous chunk consumed (and input staged on the first iteration)
+        for (int i = threadIdx.x; i < 9 * CK * CT; i += CNT) {
+            const int tap = i / (CK * CT), r = i - tap * CK * CT, c = r / CT, co = r - c * CT;
+            s_w[i] = __ldg(wpk + ((size_t)tap * CIN + c0 + c) * COUT + ct0 + co);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int c = 0; c < CK; c++) {
+            const float* ip = s_in + (c0 + c) * HP * WP;
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) {
+                const int toff = (tap / 3) * WP + (tap % 3);
+                float a[PPT];
+#pragma unroll
+                for (int k = 0; k < PPT; k++) a[k] = ip[poff[k] + toff];
+                const float4* wp = reinterpret_cast<const float4*>(s_w + (tap * CK + c) * CT + cg * CPT);
+#pragma unroll
+                for (int j4 = 0; j4 < CPT / 4; j4++) {
+                    const float4 wv = wp[j4];
+#pragma unroll
+                    for (int k = 0; k < PPT; k++) {
+                        acc[k][j4 * 4 + 0] = fmaf(a[k], wv.x, acc[k][j4 * 4 + 0]);
+                        acc[k][j4 * 4 + 1] = fmaf(a[k], wv.y, acc[k][j4 * 4 + 1]);
+                        acc[k][j4 * 4 + 2] = fmaf(a[k], wv.z, acc[k][j4 * 4 + 2]);
+                        acc[k][j4 * 4 + 3] = fmaf(a[k], wv.w, acc[k][j4 * 4 + 3]);
+                    }
+                }
+            }
+        }
+    }
+    float* dst = out + (size_t)pi * COUT * NP;
+#pragma unroll
+    for (int j = 0; j < CPT; j++)
+#pragma unroll
+        for (int k = 0; k < PPT; k++) dst[(size_t)(ct0 + cg * CPT + j) * NP + pt + k * PT] = fmaxf(acc[k][j], 0.f);
+}
+
+template <int CIN, int COUT, int HIN, int STRIDE, int CT, int CK, bool NORM>
+static int launch_conv(const float* in, float* out, const float* w, const float* b, int n, int group, const int* count,
+                       cudaStream_t st) {
+    constexpr size_t smem = sizeof(float) * ((size_t)CIN * (HIN + 2) * (HIN + 2) + 9 * CK * CT);
+    static bool configured = false;
+    auto kern = conv3x3_kernel<CIN, COUT, HIN, STRIDE, CT, CK, NORM>;
+    if (!configured) {
+        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv smem attr");
+        if (rc != AG_OK) return rc;
+        configured = true;
+    }
+    kern<<<dim3(n, COUT / CT), CNT, smem, st>>>(in, out, w, b, group, count);
+    AG_CHECK_LAUNCH("conv3x3_kernel");
+    return AG_OK;
+}
+
+// ---- heads --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// AffNet: conv8x8(64->3)+bias, tanh, A = [[1+x0, 0],[x1, 1+x2]], rectifyAffineTransformationUpIsUp (LAF.py:285-291)
+__global__ void affnet_head_kernel(const float* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
+                                   float* __restrict__ out, int n, int group, const int* __restrict__ count) {
+    const int pi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (pi >= n) return;
+    if (count != nullptr && (pi % group) >= count[pi / group]) return;
+    const float* f = feat + (size_t)pi * 4096;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < 4096; i += 32) {
+        const float v = f[i];
+        s0 = fmaf(v, __ldg(w + i), s0); s1 = fmaf(v, __ldg(w + 4096 + i), s1); s2 = fmaf(v, __ldg(w + 8192 + i), s2);
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) {
+        const float a00 = 1.0f + tanhf(s0 + bias[0]), a01 = 0.f, a10 = tanhf(s1 + bias[1]), a11 = 1.0f + tanhf(s2 + bias[2]);
+        const float det = sqrtf(fabsf(a00 * a11 - a10 * a01 + 1e-10f));
+        const float b2a2 = sqrtf(a01 * a01 + a00 * a00);
+        float* o = out + (size_t)pi * 4;
+        o[0] = b2a2 / det; o[1] = 0.f;
+        o[2] = (a11 * a01 + a10 * a00) / (b2a2 * det); o[3] = det / b2a2;
+    }
+}
+
+// OriNet: conv8x8(64->2, padding=1)+bias on the 8x8 map -> 3x3, tanh, mean, atan2, rotation (architectures.py:57-59,76-82)
+__global__ void orinet_head_kernel(const float* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
+                                   float* __restrict__ out, float* __restrict__ angle_out, int n, int group,
+                                   const int* __restrict__ count) {
+    const int pi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (pi >= n) return;
+    if (count != nullptr && (pi % group) >= count[pi / group]) return;
+    const float* f = feat + (size_t)pi * 4096;
+    float acc[2][9];
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int q = 0; q < 9; q++) acc[c][q] = 0.f;
+    for (int i = lane; i < 4096; i += 32) {
+        const int ci = i >> 6, ky = (i >> 3) & 7, kx = i & 7;
+        const float w0 = __ldg(w + i), w1 = __ldg(w + 4096 + i);
+#pragma unroll
+        for (int oy = 0; oy < 3; oy++) {
+            const int iy = oy + ky - 1;
+            if (iy < 0 || iy > 7) continue;
+#pragma unroll
+            for (int ox = 0; ox < 3; ox++) {
+                const int ix = ox + kx - 1;
+                if (ix < 0 || ix > 7) continue;
+                const float v = f[ci * 64 + iy * 8 + ix];
+                acc[0][oy * 3 + ox] = fmaf(v, w0, acc[0][oy * 3 + ox]);
+                acc[1][oy * 3 + ox] = fmaf(v, w1, acc[1][oy * 3 + ox]);
+            }
+        }
+    }
+    float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+        m0 += tanhf(warp_sum(acc[0][q]) + bias[0]);
+        m1 += tanhf(warp_sum(acc[1][q]) + bias[1]);
+    }
+    if (lane == 0) {
+        m0 /= 9.0f; m1 /= 9.0f;
+        const float ang = atan2f(m0 + 1e-8f, m1 + 1e-8f);  // architectures.py:78
+        if (angle_out) angle_out[pi] = ang;
+        if (out) {
+            const float c = cosf(ang), s = sinf(ang);  // get_rotation_matrix, LAF.py:276-283
+            float* o = out + (size_t)pi * 4;
+            o[0] = c; o[1] = s; o[2] = -s; o[3] = c;
+        }
+    }
+}
+
+// HardNet: conv8x8(128->128) == [n,8192]x[8192,128], BatchNorm, L2Norm (HardNet.py:86-101, 12-19)
+constexpr int HH_P = 16;  // patches per CTA
+__global__ void __launch_bounds__(256) hardnet_head_kernel(const float* __restrict__ feat, const float* __restrict__ w,
+                                                            const float* __restrict__ bn, float* __restrict__ out, int n,
+                                                            int group, const int* __restrict__ count) {
+    __shared__ float s_a[HH_P][64 + 1];
+    __shared__ float s_ss[HH_P][2];
+    const int p0 = blockIdx.x * HH_P;
+    const int co = threadIdx.x & 127, half = threadIdx.x >> 7;  // half: patches [half*8, half*8+8)
+    float acc[HH_P / 2];
+#pragma unroll
+    for (int k = 0; k < HH_P / 2; k++) acc[k] = 0.f;
+    for (int k0 = 0; k0 < 8192; k0 += 64) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < HH_P * 64; i += 256) {
+            const int p = i >> 6, k = i & 63;
+            s_a[p][k] = (p0 + p < n) ? feat[(size_t)(p0 + p) * 8192 + k0 + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 64; k++) {
+            const float wv = __ldg(w + (size_t)(k0 + k) * 128 + co);
+#pragma unroll
+            for (int q = 0; q < HH_P / 2; q++) acc[q] = fmaf(s_a[half * (HH_P / 2) + q][k], wv, acc[q]);
+        }
+    }
+    const float sc = bn[co], sh = bn[128 + co];
+    float v[HH_P / 2];
+#pragma unroll
+    for (int q = 0; q < HH_P / 2; q++) v[q] = fmaf(acc[q], sc, sh);
+    // sum of squares over the 128 channels of each patch: 4 warps per half
+    __syncthreads();
+    if (threadIdx.x < HH_P * 2) (&s_ss[0][0])[threadIdx.x] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < HH_P / 2; q++) {
+        const float ss = warp_sum(v[q] * v[q]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_ss[half * (HH_P / 2) + q][0], ss);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < HH_P / 2; q++) {
+        const int p = p0 + half * (HH_P / 2) + q;
+        if (p >= n) continue;
+        if (count != nullptr && (p % group) >= count[p / group]) continue;
+        out[(size_t)p * 128 + co] = v[q] / sqrtf(s_ss[half * (HH_P / 2) + q][0] + 1e-8f);
+    }
+}
+
+// ---- weight packing (host) ------------------------------------------------------------------------------
+static size_t blob_floats(int kind) {
+    const LayerCfg* cfg = (kind == AG_NET_HARDNET) ? kHardCfg : kAffCfg;
+    size_t n = 0;
+    for (int l = 0; l < 6; l++) n += (size_t)cfg[l].cout * cfg[l].cin * 9 + 2 * cfg[l].cout;
+    const int c = cfg[5].cout;
+    if (kind == AG_NET_HARDNET) n += (size_t)128 * c * 64 + 256;
+    else n += (size_t)(kind == AG_NET_AFFNET ? 3 : 2) * c * 64 + (kind == AG_NET_AFFNET ? 3 : 2);
+    return n;
+}
+
+}  // namespace ag
+
+using namespace ag;
+
+extern "C" {
+
+size_t ag_net_blob_floats(int kind) {
+    if (kind < 0 || kind > 2) return 0;
+    return blob_floats(kind);
+}
+
+int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out) {
+    AG_REQUIRE(out && h_blob, "NULL argument");
+    AG_REQUIRE(kind >= 0 && kind <= 2, "unknown net kind");
+    if (n_floats != blob_floats(kind)) {
+        set_error("ag_net_create: blob has %zu floats, kind %d needs %zu", n_floats, kind, blob_floats(kind));
+        return AG_ERR_INVALID;
+    }
+    const LayerCfg* cfg = (kind == AG_NET_HARDNET) ? kHardCfg : kAffCfg;
+    std::vector<float> packed;
+    size_t w_off[6], b_off[6], hw_off, hb_off;
+    const float* p = h_blob;
+    for (int l = 0; l < 6; l++) {
+        const int ci = cfg[l].cin, co = cfg[l].cout;
+        const float* w = p; const float* mean = w + (size_t)co * ci * 9; const float* var = mean + co;
+        p = var + co;
+        w_off[l] = packed.size();
+        packed.resize(packed.size() + (size_t)9 * ci * co);
+        float* dst = packed.data() + w_off[l];
+        std::vector<float> invstd(co);
+        for (int o = 0; o < co; o++) invstd[o] = 1.0f / sqrtf(var[o] + BN_EPS);
+        for (int tap = 0; tap < 9; tap++)
+            for (int c = 0; c < ci; c++)
+                for (int o = 0; o < co; o++) dst[((size_t)tap * ci + c) * co + o] = w[((size_t)o * ci + c) * 9 + tap] * invstd[o];
+        while (packed.size() % 4) packed.push_back(0.f);
+        b_off[l] = packed.size();
+        for (int o = 0; o < co; o++) packed.push_back(-mean[o] * invstd[o]);
+        while (packed.size() % 4) packed.push_back(0.f);
+    }
+    const int c = cfg[5].cout;
+    hw_off = packed.size();
+    if (kind == AG_NET_HARDNET) {
+        const float* w = p; const float* mean = w + (size_t)128 * c * 64; const float* var = mean + 128;
+        packed.resize(packed.size() + (size_t)8192 * 128);
+        float* dst = packed.data() + hw_off;
+        for (int o = 0; o < 128; o++)
+            for (int k = 0; k < 8192; k++) dst[(size_t)k * 128 + o] = w[(size_t)o * 8192 + k];
+        hb_off = packed.size();
+        for (int o = 0; o < 128; o++) packed.push_back(1.0f / sqrtf(var[o] + BN_EPS));
+        for (int o = 0; o < 128; o++) packed.push_back(-mean[o] / sqrtf(var[o] + BN_EPS));
+    } else {
+        const int no = (kind == AG_NET_AFFNET) ? 3 : 2;
+        const float* w = p; const float* bias = w + (size_t)no * c * 64;
+        packed.insert(packed.end(), w, w + (size_t)no * c * 64);
+        hb_off = packed.size();
+        packed.insert(packed.end(), bias, bias + no);
+        while (packed.size() % 4) packed.push_back(0.f);
+    }
+    ag_net* net = new ag_net();
+    memset(net, 0, sizeof(*net));
+    net->kind = kind;
+    int rc = check_cuda(cudaMalloc(&net->d_all, packed.size() * sizeof(float)), "cudaMalloc weights");
+    if (rc != AG_OK) { delete net; return rc; }
+    rc = check_cuda(cudaMemcpy(net->d_all, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice), "upload weights");
+    if (rc != AG_OK) { cudaFree(net->d_all); delete net; return rc; }
+    for (int l = 0; l < 6; l++) { net->d_w[l] = net->d_all + w_off[l]; net->d_b[l] = net->d_all + b_off[l]; }
+    net->d_head_w = net->d_all + hw_off;
+    net->d_head_b = net->d_all + hb_off;
+    *out = net;
+    return AG_OK;
+}
+
+void ag_net_destroy(ag_net_t* net) {
+    if (!net) return;
+    cudaFree(net->d_all);
+    delete net;
+}
+
+size_t ag_net_workspace_bytes(int kind, int n) {
+    if (n <= 0) return 0;
+    const size_t per = (kind == AG_NET_HARDNET) ? 32768 : 16384;  // largest activation per patch (floats)
+    return 2 * align_up((size_t)n * per * sizeof(float), 256);
+}
+
+}  // extern "C"
+
+namespace ag {
+
+static int trunk_affnet(const ag_net* net, const float* patches, int n, int group, const int* count, float* a, float* b,
+                        cudaStream_t st) {
+    int rc;
+    if ((rc = launch_conv<1, 16, 32, 1, 16, 1, true>(patches, a, net->d_w[0], net->d_b[0], n, group, count, st))) return rc;
+    if ((rc = launch_conv<16, 16, 32, 1, 16, 16, false>(a, b, net->d_w[1], net->d_b[1], n, group, count, st))) return rc;
+    if ((rc = launch_conv<16, 32, 32, 2, 32, 16, false>(b, a, net->d_w[2], net->d_b[2], n, group, count, st))) return rc;
+    if ((rc = launch_conv<32, 32, 16, 1, 32, 32, false>(a, b, net->d_w[3], net->d_b[3], n, group, count, st))) return rc;
+    if ((rc = launch_conv<32, 64, 16, 2, 64, 32, false>(b, a, net->d_w[4], net->d_b[4], n, group, count, st))) return rc;
+    if ((rc = launch_conv<64, 64, 8, 1, 64, 32, false>(a, b, net->d_w[5], net->d_b[5], n, group, count, st))) return rc;
+    return AG_OK;  // features in b: [n,64,8,8]
+}
+
+static int trunk_hardnet(const ag_net* net, const float* patches, int n, int group, const int* count, float* a, float* b,
+                         cudaStream_t st) {
+    int rc;
+    if ((rc = launch_conv<1, 32, 32, 1, 32, 1, true>(patches, a, net->d_w[0], net->d_b[0], n, group, count, st))) return rc;
+    if ((rc = launch_conv<32, 32, 32, 1, 32, 32, false>(a, b, net->d_w[1], net->d_b[1], n, group, count, st))) return rc;
+    if ((rc = launch_conv<32, 64, 32, 2, 64, 32, false>(b, a, net->d_w[2], net->d_b[2], n, group, count, st))) return rc;
+    if ((rc = launch_conv<64, 64, 16, 1, 64, 32, false>(a, b, net->d_w[3], net->d_b[3], n, group, count, st))) return rc;
+    if ((rc = launch_conv<64, 128, 16, 2, 128, 16, false>(b, a, net->d_w[4], net->d_b[4], n, group, count, st))) return rc;
+    if ((rc = launch_conv<128, 128, 8, 1, 128, 16, false>(a, b, net->d_w[5], net->d_b[5], n, group, count, st))) return rc;
+    return AG_OK;  // features in b: [n,128,8,8]
+}
+
+static int split_ws(int kind, int n, void* d_ws, size_t ws_bytes, float** a, float** b) {
+    const size_t need = ag_net_workspace_bytes(kind, n);
+    if (d_ws == nullptr || ws_bytes < need) {
+        set_error("net forward: workspace of %zu bytes needed, %zu given", need, ws_bytes);
+        return AG_ERR_CAPACITY;
+    }
+    *a = (float*)d_ws;
+    *b = (float*)((char*)d_ws + need / 2);
+    return AG_OK;
+}
+
+}  // namespace ag
+
+extern "C" {
+
+int ag_affnet_forward(const ag_net_t* net, const float* d_patches, int n, const int* d_count, int group, float* d_out,
+                      void* d_ws, size_t ws_bytes, void* stream) {
+    AG_REQUIRE(net && d_patches && d_out, "NULL argument");
+    AG_REQUIRE(net->kind == AG_NET_AFFNET, "not an AffNet handle");
+    if (n <= 0) return AG_OK;
+    if (group <= 0) group = n;
+    float *a, *b;
+    int rc = split_ws(net->kind, n, d_ws, ws_bytes, &a, &b);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = trunk_affnet(net, d_patches, n, group, d_count, a, b, st))) return rc;
+    affnet_head_kernel<<<cdiv(n, 8), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, n, group, d_count);
+    AG_CHECK_LAUNCH("affnet_head_kernel");
+    return AG_OK;
+}
+
+int ag_orinet_forward(const ag_net_t* net, const float* d_patches, int n, const int* d_count, int group, float* d_out,
+                      float* d_angle, void* d_ws, size_t ws_bytes, void* stream) {
+    AG_REQUIRE(net && d_patches && (d_out || d_angle), "NULL argument");
+    AG_REQUIRE(net->kind == AG_NET_ORINET, "not an OriNet handle");
+    if (n <= 0) return AG_OK;
+    if (group <= 0) group = n;
+    float *a, *b;
+    int rc = split_ws(net->kind, n, d_ws, ws_bytes, &a, &b);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = trunk_affnet(net, d_patches, n, group, d_count, a, b, st))) return rc;
+    orinet_head_kernel<<<cdiv(n, 8), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, d_angle, n, group, d_count);
+    AG_CHECK_LAUNCH("orinet_head_kernel");
+    return AG_OK;
+}
+
+int ag_hardnet_forward(const ag_net_t* net, const float* d_patches, int n, const int* d_count, int group, float* d_out,
+                       void* d_ws, size_t ws_bytes, void* stream) {
+    AG_REQUIRE(net && d_patches && d_out, "NULL argument");
+    AG_REQUIRE(net->kind == AG_NET_HARDNET, "not a HardNet handle");
+    if (n <= 0) return AG_OK;
+    if (group <= 0) group = n;
+    float *a, *b;
+    int rc = split_ws(net->kind, n, d_ws, ws_bytes, &a, &b);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = trunk_hardnet(net, d_patches, n, group, d_count, a, b, st))) return rc;
+    hardnet_head_kernel<<<cdiv(n, HH_P), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, n, group, d_count);
+    AG_CHECK_LAUNCH("hardnet_head_kernel");
+    return AG_OK;
+}
+
+}  // extern "C"

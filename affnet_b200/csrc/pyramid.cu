@@ -1,0 +1,257 @@
+// Gaussian scale-space pyramid.
+//
+// Replaces ScalePyramid.forward (HandCraftedModules.py:13-56) and GaussianBlur (Utils.py:92-114,150-166).
+// The reference convolves with a dense k x k kernel that is an exact outer product (Q1), so each blur
+// is done here as a fused horizontal+vertical separable pass through shared memory: one HBM/L2 read of
+// the source tile (+halo), one write of the blurred tile, and - for the level that seeds the next
+// octave - the stride-2 decimated copy (F.avg_pool2d(k=1, s=2)) from the same registers.
+#include <math.h>
+#include <stdarg.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ag {
+
+static thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- per-launch CUDA-event profiler (bench.py's roofline leg) ---------------------------------------
+struct Prof {
+    bool on = false;
+    cudaStream_t st = nullptr;
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::string> names;
+    std::vector<float> ms;
+};
+static Prof g_prof;
+
+void prof_mark(const char* name) {
+    if (!g_prof.on) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, g_prof.st);
+    g_prof.ev.push_back(e);
+    g_prof.names.push_back(name);
+}
+
+// ---- host: kernel taps exactly as CircularGaussKernel builds them (float64 -> float32) -------------
+constexpr int kMaxRadius = 12;  // sigma up to ~4.0
+struct BlurTaps {
+    int r;
+    float w[2 * kMaxRadius + 1];
+};
+
+int gauss_kernel_size(double sigma) {  // Utils.py:95-97
+    int k = (int)(2.0 * 3.0 * sigma + 1.0);
+    if (k % 2 == 0) k += 1;
+    return k;
+}
+
+int make_taps(double sigma, BlurTaps* t) {
+    int k = gauss_kernel_size(sigma);
+    if (k < 1 || k > 2 * kMaxRadius + 1) {
+        set_error("gaussian sigma %.4f needs %d taps (max %d)", sigma, k, 2 * kMaxRadius + 1);
+        return AG_ERR_INVALID;
+    }
+    // Utils.py:98-113 under python3: halfSize = k/2 (true division), x = linspace(-half, half, k)
+    double half = k / 2.0, e[2 * kMaxRadius + 1], sum = 0.0;
+    double step = (k > 1) ? (2.0 * half) / (k - 1) : 0.0;
+    for (int i = 0; i < k; i++) {
+        double x = (i == k - 1) ? half : -half + i * step;
+        e[i] = exp(-(x * x) / (2.0 * sigma * sigma));
+        sum += e[i];
+    }
+    t->r = k / 2;
+    for (int i = 0; i < k; i++) t->w[i] = (float)(e[i] / sum);
+    return AG_OK;
+}
+
+// ---- device: fused separable blur ---------------------------------------------------------------
+constexpr int TW = 64, TH = 32, NT = 256;
+
+template <int R>
+__global__ void __launch_bounds__(NT) blur_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                   float* __restrict__ dec, int h, int w, BlurTaps taps) {
+    constexpr int IW = TW + 2 * R, IH = TH + 2 * R;
+    __shared__ float s_in[IH][IW + 1];
+    __shared__ float s_mid[IH][TW];
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const float* img = in + (size_t)b * h * w;
+    // 1. load tile + halo with replicate (clamp) addressing
+    for (int i = threadIdx.x; i < IH * IW; i += NT) {
+        int ly = i / IW, lx = i - ly * IW;
+        int gy = clampi(y0 + ly - R, 0, h - 1), gx = clampi(x0 + lx - R, 0, w - 1);
+        s_in[ly][lx] = __ldg(img + (size_t)gy * w + gx);
+    }
+    __syncthreads();
+    // 2. horizontal pass on all IH rows
+    for (int i = threadIdx.x; i < IH * TW; i += NT) {
+        int ly = i / TW, lx = i - ly * TW;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k <= 2 * R; k++) acc = fmaf(taps.w[k], s_in[ly][lx + k], acc);
+        s_mid[ly][lx] = acc;
+    }
+    __syncthreads();
+    // 3. vertical pass + store (+ decimated copy)
+    const int h2 = (h + 1) >> 1, w2 = (w + 1) >> 1;
+    for (int i = threadIdx.x; i < TH * TW; i += NT) {
+        int ly = i / TW, lx = i - ly * TW;
+        int gy = y0 + ly, gx = x0 + lx;
+        if (gy >= h || gx >= w) continue;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k <= 2 * R; k++) acc = fmaf(taps.w[k], s_mid[ly + k][lx], acc);
+        out[(size_t)b * h * w + (size_t)gy * w + gx] = acc;
+        if (dec != nullptr && ((gy | gx) & 1) == 0) dec[(size_t)b * h2 * w2 + (size_t)(gy >> 1) * w2 + (gx >> 1)] = acc;
+    }
+}
+
+static int launch_blur(const float* in, float* out, float* dec, int B, int h, int w, double sigma, cudaStream_t st) {
+    BlurTaps taps;
+    int rc = make_taps(sigma, &taps);
+    if (rc != AG_OK) return rc;
+    dim3 grid(cdiv(w, TW), cdiv(h, TH), B), block(NT);
+    switch (taps.r) {
+#define AG_BLUR_CASE(R)                                                  \
+    case R:                                                              \
+        blur_kernel<R><<<grid, block, 0, st>>>(in, out, dec, h, w, taps); \
+        break;
+        AG_BLUR_CASE(1) AG_BLUR_CASE(2) AG_BLUR_CASE(3) AG_BLUR_CASE(4) AG_BLUR_CASE(5) AG_BLUR_CASE(6)
+        AG_BLUR_CASE(7) AG_BLUR_CASE(8) AG_BLUR_CASE(9) AG_BLUR_CASE(10) AG_BLUR_CASE(11) AG_BLUR_CASE(12)
+#undef AG_BLUR_CASE
+        default:
+            set_error("unsupported blur radius %d", taps.r);
+            return AG_ERR_INVALID;
+    }
+    AG_CHECK_LAUNCH("blur_kernel");
+    return AG_OK;
+}
+
+__global__ void decimate_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w, int h2, int w2) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x < w2) out[(size_t)b * h2 * w2 + (size_t)y * w2 + x] = in[(size_t)b * h * w + (size_t)(2 * y) * w + 2 * x];
+}
+
+}  // namespace ag
+
+using namespace ag;
+
+extern "C" {
+
+const char* ag_last_error(void) { return ag::g_err; }
+int ag_abi_version(void) { return 1; }
+
+int ag_prof_begin(void* stream) {
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.clear(); g_prof.names.clear(); g_prof.ms.clear();
+    g_prof.st = (cudaStream_t)stream;
+    g_prof.on = true;
+    prof_mark("<begin>");
+    return AG_OK;
+}
+
+int ag_prof_end(void) {
+    g_prof.on = false;
+    if (g_prof.ev.empty()) return 0;
+    int rc = check_cuda(cudaEventSynchronize(g_prof.ev.back()), "prof sync");
+    if (rc != AG_OK) return rc;
+    g_prof.ms.assign(g_prof.ev.size(), 0.f);
+    for (size_t i = 1; i < g_prof.ev.size(); i++) cudaEventElapsedTime(&g_prof.ms[i], g_prof.ev[i - 1], g_prof.ev[i]);
+    return (int)g_prof.ev.size() - 1;
+}
+
+int ag_prof_get(int i, const char** name, float* ms) {
+    AG_REQUIRE(i >= 0 && (size_t)(i + 1) < g_prof.ev.size() && name && ms, "index out of range");
+    *name = g_prof.names[i + 1].c_str();
+    *ms = g_prof.ms[i + 1];
+    return AG_OK;
+}
+
+int ag_pyramid_plan(int B, int H, int W, int nlevels, double init_sigma, int border, ag_pyramid_plan_t* plan) {
+    AG_REQUIRE(plan != nullptr, "plan is NULL");
+    AG_REQUIRE(B >= 1 && H >= 1 && W >= 1, "bad image size");
+    AG_REQUIRE(nlevels >= 1 && nlevels + 2 <= AG_MAX_LEVELS, "nlevels out of range");
+    memset(plan, 0, sizeof(*plan));
+    plan->B = B; plan->H = H; plan->W = W;
+    plan->n_levels = nlevels + 2;
+    // HandCraftedModules.py:15-22
+    const double sigma_step = pow(2.0, 1.0 / (double)nlevels);
+    const int min_size = 2 * border + 2 + 1;
+    double cur_sigma = 0.5, first = 0.0, pd = 1.0;
+    if (init_sigma > cur_sigma) {
+        first = sqrt(init_sigma * init_sigma - cur_sigma * cur_sigma);
+        cur_sigma = init_sigma;
+    }
+    int h = H, w = W, o = 0;
+    long long off = 0;
+    for (;;) {
+        AG_REQUIRE(o < AG_MAX_OCTAVES, "too many octaves");
+        plan->h[o] = h; plan->w[o] = w; plan->pix_dist[o] = pd;
+        plan->sigma[o][0] = cur_sigma;
+        plan->blur_sigma[o][0] = (o == 0) ? first : 0.0;
+        for (int l = 0; l < plan->n_levels; l++) {
+            plan->level_offset[o][l] = off;
+            off += (long long)B * h * w;
+        }
+        for (int i = 1; i < plan->n_levels; i++) {  // HandCraftedModules.py:38-45
+            plan->blur_sigma[o][i] = cur_sigma * sqrt(sigma_step * sigma_step - 1.0);
+            cur_sigma = cur_sigma * sigma_step;
+            plan->sigma[o][i] = cur_sigma;
+        }
+        o++;
+        pd *= 2.0;
+        cur_sigma = init_sigma;
+        int nh = (h + 1) / 2, nw = (w + 1) / 2;
+        if (nh <= min_size || nw <= min_size) break;  // HandCraftedModules.py:50
+        h = nh; w = nw;
+    }
+    plan->n_octaves = o;
+    plan->total_floats = off;
+    return AG_OK;
+}
+
+int ag_gaussian_blur(const float* d_in, float* d_out, int B, int h, int w, double sigma, void* stream) {
+    AG_REQUIRE(d_in && d_out && B >= 1 && h >= 1 && w >= 1, "bad arguments");
+    return launch_blur(d_in, d_out, nullptr, B, h, w, sigma, (cudaStream_t)stream);
+}
+
+int ag_pyramid_build(const ag_pyramid_plan_t* p, const float* d_img, float* d_pyr, void* stream) {
+    AG_REQUIRE(p && d_img && d_pyr, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nl = p->n_levels, seed_level = nl - 2;  // level `nlevels` seeds the next octave (:46-47)
+    for (int o = 0; o < p->n_octaves; o++) {
+        const int h = p->h[o], w = p->w[o];
+        float* lvl0 = d_pyr + p->level_offset[o][0];
+        if (o == 0) {
+            if (p->blur_sigma[0][0] > 0.0) {
+                int rc = launch_blur(d_img, lvl0, nullptr, p->B, h, w, p->blur_sigma[0][0], st);
+                if (rc != AG_OK) return rc;
+            } else {
+                int rc = check_cuda(cudaMemcpyAsync(lvl0, d_img, sizeof(float) * (size_t)p->B * h * w,
+                                                    cudaMemcpyDeviceToDevice, st), "copy level 0");
+                if (rc != AG_OK) return rc;
+            }
+        }
+        for (int l = 1; l < nl; l++) {
+            float* dec = (l == seed_level && o + 1 < p->n_octaves) ? d_pyr + p->level_offset[o + 1][0] : nullptr;
+            int rc = launch_blur(d_pyr + p->level_offset[o][l - 1], d_pyr + p->level_offset[o][l], dec, p->B, h, w,
+                                 p->blur_sigma[o][l], st);
+            if (rc != AG_OK) return rc;
+        }
+    }
+    return AG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+"""Batched detect-and-describe for B same-sized images (new API; the reference handles one image at a time):
+the whole ScaleSpaceAffinePatchExtractor.forward + extract_patches_from_pyr + HardNet chain as one fixed kernel
+sequence with device-side counters, optionally replayed as a CUDA graph."""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+class DetectDescribePipeline:
+    def __init__(self, B, H, W, AffNet, HardNet, OriNet=None, num_features=2000, border=5, mrSize=5.192, nlevels=3,
+                 init_sigma=1.6, do_ori=True, cand_cap=0, device="cuda"):
+        self.cfg = L.PipelineConfig(B, H, W, num_features, nlevels, border, float(init_sigma), float(mrSize), 1 if do_ori else 0, cand_cap)
+        self.nets = (AffNet, OriNet, HardNet)  # keep the handles alive
+        h = C.c_void_p()
+        L.check(L.lib().ag_pipeline_create(C.byref(self.cfg), AffNet.handle(), OriNet.handle() if OriNet is not None else None,
+                                           HardNet.handle(), C.byref(h)))
+        self._h = h
+        self.B, self.H, self.W, self.K = B, H, W, num_features
+        self.device = torch.device(device)
+        self.ws_bytes = L.lib().ag_pipeline_workspace_bytes(h)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self.lafs = torch.empty(B, num_features, 2, 3, dtype=torch.float32, device=self.device)
+        self.resp = torch.empty(B, num_features, dtype=torch.float32, device=self.device)
+        self.desc = torch.empty(B, num_features, 128, dtype=torch.float32, device=self.device)
+        self.count = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._graph = None
+        self._static_in = None
+
+    def __del__(self):
+        try:
+            L.lib().ag_pipeline_destroy(self._h)
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return L.lib().ag_pipeline_launch_count(self._h)
+
+    def run(self, imgs):
+        """imgs CUDA float32 [B,1,H,W] or [B,H,W] -> (lafs [B,K,2,3] px, resp [B,K], desc [B,K,128], count [B]).
+        Rows >= count[b] are unspecified.  No host synchronisation."""
+        imgs = L.f32c(imgs, "imgs")
+        if imgs.numel() != self.B * self.H * self.W:
+            raise L.AffnetB200Error("expected %d x %d x %d pixels" % (self.B, self.H, self.W))
+        L.check(L.lib().ag_pipeline_run(self._h, L.ptr(imgs), L.ptr(self.ws), self.ws_bytes, L.ptr(self.lafs), L.ptr(self.resp),
+                                        L.ptr(self.desc), L.ptr(self.count), L.stream_ptr()))
+        return self.lafs, self.resp, self.desc, self.count
+
+    def capture(self):
+        """Capture one run() into a CUDA graph over a static input buffer; use replay(imgs) afterwards."""
+        self._static_in = torch.zeros(self.B, 1, self.H, self.W, dtype=torch.float32, device=self.device)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.run(self._static_in)  # warm-up: sets kernel attributes outside capture
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run(self._static_in)
+        self._graph = g
+        return self
+
+    def replay(self, imgs=None):
+        if self._graph is None:
+            raise L.AffnetB200Error("call capture() first")
+        if imgs is not None:
+            self._static_in.copy_(imgs.view_as(self._static_in), non_blocking=True)
+        self._graph.replay()
+        return self.lafs, self.resp, self.desc, self.count

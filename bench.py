@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the HesAffNet + HardNet detect-and-describe hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+One "step" = one pass of the whole path (pyramid -> Hessian/NMS -> top-k -> sample -> AffNet -> filter -> sample
+-> OriNet -> sample -> HardNet) over one batch of B synthetic 1024x768 images, K=2000 keypoints each, per GPU
+(BASELINE.json configs[1] tiled B times = configs[3]'s per-GPU shard).  N>1: one process per GPU (torchrun), B
+images per rank (weak scaling), one NCCL all-gather of descriptors/LAFs/counts per step.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H, W, K = 768, 1024, 2000
+ALG_BYTES_PER_PX = 30.66                      # detect stage, 4 B read + 5 levels x 4 B x 1.333 written
+FLOP_PER_PATCH = {"affnet": 19.19e6, "orinet": 19.32e6, "hardnet": 78.18e6}   # 2*MAC, SURVEY.md §8(d)
+# 2*MAC of each conv layer kernel, per patch (for the per-kernel roofline)
+HARD_LAYER_FLOP = [2 * 294912, 2 * 9437184, 2 * 4718592, 2 * 9437184, 2 * 4718592, 2 * 9437184, 2 * 1048576]
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+def make_images(B, seed0):
+    import affnet_oracle as O
+    return torch.cat([O.synthetic_image(H, W, seed0 + i) for i in range(B)])
+
+
+def load_state_dicts():
+    from helpers import load_weights
+    return load_weights()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s, p in zip(sm, pw) if p > 250] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_leg(n_images, threads):
+    """The reference's algorithm on host cores: oracle port (oracle/affnet_oracle.py), all cores."""
+    import affnet_oracle as O
+    torch.set_num_threads(threads)
+    sd = load_state_dicts()
+    imgs = make_images(n_images, 1234)
+    O.detect_and_describe(imgs[0:1], sd["affnet"], sd["orinet"], sd["hardnet"], K, do_ori=True)  # warm-up
+    t0 = time.perf_counter()
+    n_desc = 0
+    for i in range(n_images):
+        dL, r, d = O.detect_and_describe(imgs[i:i + 1], sd["affnet"], sd["orinet"], sd["hardnet"], K, do_ori=True)
+        n_desc += d.shape[0]
+    dt = time.perf_counter() - t0
+    return dt, n_images * H * W / dt / 1e6, n_desc / dt / 1e3
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per = max(1, args.ref_images)
+    for _ in range(args.warmup):
+        pass  # cpu_reference_leg warms up once per call
+    times, mpix, kp = [], [], []
+    for _ in range(max(1, args.steps)):
+        dt, m, k = cpu_reference_leg(per, threads)
+        times.append(dt); mpix.append(m); kp.append(k)
+    v = float(np.mean(mpix))
+    line = {"impl": "reference", "metric": "Mpix/s end-to-end HesAffNet(+OriNet)+HardNet", "value": v, "unit": "Mpix/s",
+            "kpatches_per_s": float(np.mean(kp)), "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic images (seeded noise, blur sigma 2, stretched), pretrained weights from tests/golden",
+            "config": {"workload": "%dx%d grayscale, %d kpts/img, %d image(s) per step (bounded CPU sample of the batch)" % (W, H, K, per),
+                       "do_ori": True, "border": 5, "mrSize": 5.192},
+            "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": threads, "kind": "port",
+                             "sample": "%d image(s) of the workload per step, oracle/affnet_oracle.py (PyTorch-CPU restatement; the reference itself is Python and cannot travel)" % per},
+            "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-images", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+
+    import affnet_b200._lib as L
+    from affnet_b200.architectures import AffNetFast, OriNetFast
+    from affnet_b200.HardNet import HardNet
+    from affnet_b200.pipeline import DetectDescribePipeline
+    sd = load_state_dicts()
+    a, o, h = AffNetFast(PS=32), OriNetFast(PS=32), HardNet()
+    a.load_state_dict(sd["affnet"]); o.load_state_dict(sd["orinet"]); h.load_state_dict(sd["hardnet"])
+    a, o, h = a.eval().to(dev), o.eval().to(dev), h.eval().to(dev)
+    B = args.batch
+    pipe = DetectDescribePipeline(B, H, W, a, h, o, num_features=K, do_ori=True, device=dev)
+    host_imgs = make_images(B, 1234 + rank * B).pin_memory()
+    dev_imgs = host_imgs.to(dev)
+    host_desc = torch.empty(B, K, 128).pin_memory(); host_lafs = torch.empty(B, K, 2, 3).pin_memory()
+    host_resp = torch.empty(B, K).pin_memory(); host_cnt = torch.empty(B, dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+    gather = None
+    if world > 1:
+        gather = [torch.empty(world * B, K, 128, device=dev), torch.empty(world * B, K, 2, 3, device=dev), torch.empty(world * B, dtype=torch.int32, device=dev)]
+
+    use_graph = not args.no_graph
+    if use_graph:
+        pipe.capture()
+
+    def step_device():
+        if use_graph:
+            out = pipe.replay(dev_imgs)
+        else:
+            out = pipe.run(dev_imgs)
+        if world > 1:
+            dist.all_gather_into_tensor(gather[0], out[2]); dist.all_gather_into_tensor(gather[1], out[0]); dist.all_gather_into_tensor(gather[2], out[3])
+        return out
+
+    def step_e2e():
+        x = host_imgs.to(dev, non_blocking=True)
+        out = pipe.replay(x) if use_graph else pipe.run(x)
+        if world > 1:
+            dist.all_gather_into_tensor(gather[0], out[2]); dist.all_gather_into_tensor(gather[1], out[0]); dist.all_gather_into_tensor(gather[2], out[3])
+        host_desc.copy_(out[2], non_blocking=True); host_lafs.copy_(out[0], non_blocking=True)
+        host_resp.copy_(out[1], non_blocking=True); host_cnt.copy_(out[3], non_blocking=True)
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1.0)                                  # L2 flush between timed iterations (outside the events)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = sum(a_.elapsed_time(b_) for a_, b_ in evs)
+        t = torch.tensor([total_ms], device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), clocks
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    total_ms, clocks = timed(step_device, args.steps, args.warmup, sampler)
+    n_desc = int(pipe.count.sum().item())
+    e2e_ms, _ = timed(step_e2e, args.steps, args.warmup)
+
+    # ---- per-kernel CUDA-event profile of the same step (non-graph launch path), rank 0 ---------------------------
+    roof = None
+    if rank == 0:
+        per_kernel = {}
+        prof_steps = 3
+        for _ in range(prof_steps):
+            flush.fill_(1.0)
+            for name, ms in L.profile(lambda: pipe.run(dev_imgs)):
+                per_kernel.setdefault(name, []).append(ms)
+        step_ms = sum(sum(v) for v in per_kernel.values()) / prof_steps
+        agg = sorted(((sum(v) / prof_steps, len(v) // prof_steps, k) for k, v in per_kernel.items()), reverse=True)
+        pk = peaks()
+        top_ms, top_n, top_name = agg[0]
+        # dominant kernel family: the direct 3x3 convolutions of the three CNN trunks (18 launches / step)
+        n_aff, n_ori, n_hard = B * int(1.5 * K), n_desc, n_desc
+        conv_flop = n_aff * (FLOP_PER_PATCH["affnet"] - 2 * 3 * 4096) + n_ori * (FLOP_PER_PATCH["orinet"] - 2 * 2 * 9 * 4096) + n_hard * (FLOP_PER_PATCH["hardnet"] - HARD_LAYER_FLOP[6])
+        conv_ms = sum(t for t, n, k in agg if k == "conv3x3_kernel")
+        ach = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        roof = {"kernel": "conv3x3_kernel (18 launches/step: AffNet, OriNet, HardNet trunks)", "bound": "tensor", "achieved": ach,
+                "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"], "traffic": None,
+                "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)", "kernel_ms_per_step": conv_ms,
+                "share_of_step": conv_ms / step_ms if step_ms else None,
+                "timing": "CUDA events after every launch over %d profiled steps right after the timed region" % prof_steps,
+                "stages_ms": {k: round(t, 4) for t, n, k in agg}}
+        # HBM roofline of the stencil side (pyramid + detect kernels), reported alongside
+        st_ms = sum(t for t, n, k in agg if k in ("blur_kernel", "detect_level_kernel"))
+        roof["stencil"] = {"kernels": "blur_kernel x25 + detect_level_kernel x3", "bound": "hbm", "achieved": ALG_BYTES_PER_PX * B * H * W / (st_ms * 1e-3) / 1e9 if st_ms else None,
+                           "peak": pk["hbm"], "unit": "GB/s", "ms_per_step": st_ms}
+        if roof["stencil"]["achieved"]:
+            roof["stencil"]["frac"] = roof["stencil"]["achieved"] / pk["hbm"]
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        dt, m, kps = cpu_reference_leg(args.ref_images, threads)
+        cpu = {"value": m, "unit": "Mpix/s", "cores": threads, "kind": "port", "kpatches_per_s": kps,
+               "sample": "%d of the %d images of one step, oracle/affnet_oracle.py on all host cores (%.1f s)" % (args.ref_images, B, dt)}
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        pix = world * B * H * W
+        value = pix / (ms_per_step * 1e-3) / 1e6
+        e2e_v = pix / (e2e_ms / args.steps * 1e-3) / 1e6
+        line = {"metric": "Mpix/s end-to-end HesAffNet(+OriNet)+HardNet", "value": value, "unit": "Mpix/s",
+                "kpatches_per_s": world * n_desc / (ms_per_step * 1e-3) / 1e3, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic images (seeded noise, blur sigma 2, stretched), pretrained weights from tests/golden",
+                "config": {"workload": "%dx%d grayscale, %d kpts/img, batch of %d images per GPU per step (configs[1] tiled = configs[3] shard)" % (W, H, K, B),
+                           "do_ori": True, "border": 5, "mrSize": 5.192, "cuda_graph": use_graph, "l2": "256 MiB flush write between timed steps",
+                           "parallelism": "images sharded across GPUs, NCCL all-gather of descriptors/LAFs/counts per step" if world > 1 else "single GPU"},
+                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+                "e2e": {"value": e2e_v, "unit": "Mpix/s", "h2d_bytes_per_step": B * H * W * 4,
+                        "d2h_bytes_per_step": B * K * (128 + 6 + 1) * 4 + B * 4, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": pipe.launches * args.steps, "launches_per_step": pipe.launches,
+                "descriptors_per_step": world * n_desc}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
