@@ -536,7 +536,7 @@ int ag_select_keypoints(const ag_pyramid_plan_t* p, const ag_detect_ws_t* ws, in
         return AG_ERR_CAPACITY;
     }
     static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 32 * 1024 && smem > configured) {  // static + dynamic must stay under the 48 KiB default
         int rc = check_cuda(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "select smem attr");
         if (rc != AG_OK) return rc;
         configured = smem;

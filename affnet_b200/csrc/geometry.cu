@@ -161,7 +161,7 @@ int ag_affine_shape_filter(const float* d_A, const float* d_resp, const float* d
         return AG_ERR_CAPACITY;
     }
     static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 32 * 1024 && smem > configured) {  // static + dynamic must stay under the 48 KiB default
         int rc = check_cuda(cudaFuncSetAttribute(shape_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "shape smem attr");
         if (rc != AG_OK) return rc;
         configured = smem;

@@ -238,7 +238,6 @@ __global__ void __launch_bounds__(256) hardnet_head_kernel(const float* __restri
                                                             const float* __restrict__ bn, float* __restrict__ out, int n,
                                                             int group, const int* __restrict__ count) {
     __shared__ float s_a[HH_P][64 + 1];
-    __shared__ float s_ss[HH_P][2];
     const int p0 = blockIdx.x * HH_P;
     const int co = threadIdx.x & 127, half = threadIdx.x >> 7;  // half: patches [half*8, half*8+8)
     float acc[HH_P / 2];
@@ -262,22 +261,22 @@ __global__ void __launch_bounds__(256) hardnet_head_kernel(const float* __restri
     float v[HH_P / 2];
 #pragma unroll
     for (int q = 0; q < HH_P / 2; q++) v[q] = fmaf(acc[q], sc, sh);
-    // sum of squares over the 128 channels of each patch: 4 warps per half
+    // sum of squares over the 128 channels of each patch: 4 warps per half, combined in a fixed order
     __syncthreads();
-    if (threadIdx.x < HH_P * 2) (&s_ss[0][0])[threadIdx.x] = 0.f;
-    __syncthreads();
+    const int wih = (threadIdx.x >> 5) & 3;  // warp index within the half
 #pragma unroll
     for (int q = 0; q < HH_P / 2; q++) {
         const float ss = warp_sum(v[q] * v[q]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&s_ss[half * (HH_P / 2) + q][0], ss);
+        if ((threadIdx.x & 31) == 0) s_a[half * (HH_P / 2) + q][wih] = ss;
     }
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < HH_P / 2; q++) {
-        const int p = p0 + half * (HH_P / 2) + q;
+        const int r = half * (HH_P / 2) + q, p = p0 + r;
         if (p >= n) continue;
         if (count != nullptr && (p % group) >= count[p / group]) continue;
-        out[(size_t)p * 128 + co] = v[q] / sqrtf(s_ss[half * (HH_P / 2) + q][0] + 1e-8f);
+        const float ss = (s_a[r][0] + s_a[r][1]) + (s_a[r][2] + s_a[r][3]);
+        out[(size_t)p * 128 + co] = v[q] / sqrtf(ss + 1e-8f);
     }
 }
 
