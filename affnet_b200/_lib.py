@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libaffnet_b200.so")
 AG_MAX_OCTAVES, AG_MAX_LEVELS = 16, 8
 NET_AFFNET, NET_ORINET, NET_HARDNET = 0, 1, 2
+ENGINE_SIMT, ENGINE_TC = 0, 1
 
 
 class AffnetB200Error(RuntimeError):
@@ -71,6 +72,8 @@ PROTOTYPES = {
     "ag_net_create": (i32, [i32, vp, sz, C.POINTER(vp)]),
     "ag_net_destroy": (None, [vp]),
     "ag_net_blob_floats": (sz, [i32]),
+    "ag_net_set_engine": (i32, [vp, i32]),
+    "ag_net_get_engine": (i32, [vp]),
     "ag_net_workspace_bytes": (sz, [i32, i32]),
     "ag_affnet_forward": (i32, [vp, vp, i32, vp, i32, vp, vp, sz, vp]),
     "ag_orinet_forward": (i32, [vp, vp, i32, vp, i32, vp, vp, vp, sz, vp]),

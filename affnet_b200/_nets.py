@@ -28,6 +28,7 @@ class _NativeNet(nn.Module):
         super().__init__()
         self._handle = None
         self._handle_key = None
+        self._engine = None   # None = library default (HardNet: tensor cores, AffNet/OriNet: exact fp32)
 
     # -- weights ------------------------------------------------------------------------------------------
     def _blob(self):
@@ -54,7 +55,20 @@ class _NativeNet(nn.Module):
             h = C.c_void_p()
             L.check(L.lib().ag_net_create(self.KIND, C.c_void_p(blob.data_ptr()), blob.numel(), C.byref(h)))
             self._handle, self._handle_key = h, key
+            if self._engine is not None:
+                L.check(L.lib().ag_net_set_engine(h, self._engine))
         return self._handle
+
+    def set_engine(self, engine):
+        """engine: L.ENGINE_SIMT (exact fp32) or L.ENGINE_TC (tcgen05, fp16 operands / fp32 accumulate)."""
+        self._engine = engine
+        if self._handle is not None:
+            L.check(L.lib().ag_net_set_engine(self._handle, engine))
+        return self
+
+    @property
+    def engine(self):
+        return L.lib().ag_net_get_engine(self.handle())
 
     def _release(self):
         if self._handle is not None:

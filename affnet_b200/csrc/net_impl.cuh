@@ -1,0 +1,31 @@
+// Internal definition of the opaque ag_net_t handle shared by the fp32 SIMT engine (nets_simt.cu) and the
+// tensor-core engine (nets_tc.cu).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+#define AG_ENGINE_SIMT 0  /* exact fp32 direct convolution */
+#define AG_ENGINE_TC 1    /* tcgen05: fp16 operands, fp32 accumulate; layer 1 and heads in fp32 */
+
+struct ag_net {
+    int kind;
+    int engine;
+    float* d_w[6];     // fp32 [9][cin][cout], BN folded   (d_w[0] doubles as the [9][C] first-layer weights)
+    float* d_b[6];     // fp32 [cout]  (BN shift)
+    float* d_w1;       // == d_w[0]
+    __half* d_wh[6];   // fp16 [nsplit][9][cin/8][cout/nsplit][8] for layers 1..5 (index 0 unused)
+    float* d_head_w;   // AffNet [3][4096], OriNet [2][4096], HardNet [8192][128]
+    float* d_head_b;   // AffNet bias[3], OriNet bias[2], HardNet {scale[128], shift[128]}
+    float* d_all;      // fp32 allocation
+    __half* d_all_h;   // fp16 allocation
+};
+
+namespace ag {
+size_t tc_act_bytes(int kind);
+int tc_nsplit(int kind, int layer);
+int tc_trunk_hardnet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
+                     cudaStream_t st);
+int tc_trunk_affnet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
+                    cudaStream_t st);
+}  // namespace ag

@@ -10,7 +10,7 @@
 
 #include <vector>
 
-#include "common.cuh"
+#include "net_impl.cuh"
 
 namespace ag {
 
@@ -24,15 +24,6 @@ static const LayerCfg kAffCfg[6] = {{1, 16, 1, 32}, {16, 16, 1, 32}, {16, 32, 2,
 static const LayerCfg kHardCfg[6] = {{1, 32, 1, 32}, {32, 32, 1, 32}, {32, 64, 2, 32}, {64, 64, 1, 16}, {64, 128, 2, 16}, {128, 128, 1, 8}};
 
 }  // namespace ag
-
-struct ag_net {
-    int kind;
-    float* d_w[6];     // [9][cin][cout], BN folded
-    float* d_b[6];     // [cout]
-    float* d_head_w;   // AffNet [3][4096], OriNet [2][4096], HardNet [8192][128]
-    float* d_head_b;   // AffNet bias[3], OriNet bias[2], HardNet {scale[128], shift[128]}
-    float* d_all;      // single allocation backing everything
-};
 
 namespace ag {
 
@@ -349,14 +340,40 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
         packed.insert(packed.end(), bias, bias + no);
         while (packed.size() % 4) packed.push_back(0.f);
     }
+    // fp16 packs for the tensor-core engine: [nsplit][9][cin/8][cout/nsplit][8], layers 1..5
+    std::vector<__half> packed_h;
+    size_t wh_off[6] = {0, 0, 0, 0, 0, 0};
+    for (int l = 1; l < 6; l++) {
+        const int ci = cfg[l].cin, co = cfg[l].cout, ns = tc_nsplit(kind, l), nt = co / ns, kc = ci / 8;
+        const float* wf = packed.data() + w_off[l];  // [tap][ci][co]
+        wh_off[l] = packed_h.size();
+        packed_h.resize(packed_h.size() + (size_t)9 * ci * co);
+        __half* dst = packed_h.data() + wh_off[l];
+        for (int sp = 0; sp < ns; sp++)
+            for (int tap = 0; tap < 9; tap++)
+                for (int g = 0; g < kc; g++)
+                    for (int nn = 0; nn < nt; nn++)
+                        for (int e = 0; e < 8; e++)
+                            dst[((((size_t)sp * 9 + tap) * kc + g) * nt + nn) * 8 + e] =
+                                __float2half_rn(wf[((size_t)tap * ci + g * 8 + e) * co + sp * nt + nn]);
+    }
     ag_net* net = new ag_net();
     memset(net, 0, sizeof(*net));
     net->kind = kind;
+    net->engine = (kind == AG_NET_HARDNET) ? AG_ENGINE_TC : AG_ENGINE_SIMT;
+    {
+        int rch = check_cuda(cudaMalloc(&net->d_all_h, packed_h.size() * sizeof(__half)), "cudaMalloc fp16 weights");
+        if (rch != AG_OK) { delete net; return rch; }
+        rch = check_cuda(cudaMemcpy(net->d_all_h, packed_h.data(), packed_h.size() * sizeof(__half), cudaMemcpyHostToDevice), "upload fp16 weights");
+        if (rch != AG_OK) { cudaFree(net->d_all_h); delete net; return rch; }
+        for (int l = 1; l < 6; l++) net->d_wh[l] = net->d_all_h + wh_off[l];
+    }
     int rc = check_cuda(cudaMalloc(&net->d_all, packed.size() * sizeof(float)), "cudaMalloc weights");
-    if (rc != AG_OK) { delete net; return rc; }
+    if (rc != AG_OK) { cudaFree(net->d_all_h); delete net; return rc; }
     rc = check_cuda(cudaMemcpy(net->d_all, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice), "upload weights");
-    if (rc != AG_OK) { cudaFree(net->d_all); delete net; return rc; }
+    if (rc != AG_OK) { cudaFree(net->d_all); cudaFree(net->d_all_h); delete net; return rc; }
     for (int l = 0; l < 6; l++) { net->d_w[l] = net->d_all + w_off[l]; net->d_b[l] = net->d_all + b_off[l]; }
+    net->d_w1 = net->d_w[0];
     net->d_head_w = net->d_all + hw_off;
     net->d_head_b = net->d_all + hb_off;
     *out = net;
@@ -366,8 +383,18 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
 void ag_net_destroy(ag_net_t* net) {
     if (!net) return;
     cudaFree(net->d_all);
+    cudaFree(net->d_all_h);
     delete net;
 }
+
+int ag_net_set_engine(ag_net_t* net, int engine) {
+    AG_REQUIRE(net != nullptr, "NULL net");
+    AG_REQUIRE(engine == AG_ENGINE_SIMT || engine == AG_ENGINE_TC, "unknown engine");
+    net->engine = engine;
+    return AG_OK;
+}
+
+int ag_net_get_engine(const ag_net_t* net) { return net ? net->engine : -1; }
 
 size_t ag_net_workspace_bytes(int kind, int n) {
     if (n <= 0) return 0;
@@ -403,6 +430,28 @@ static int trunk_hardnet(const ag_net* net, const float* patches, int n, int gro
     return AG_OK;  // features in b: [n,128,8,8]
 }
 
+// Runs the six conv layers with the net's engine; *feat receives the fp32 NCHW feature pointer ([n,C,8,8]).
+static int run_trunk(const ag_net* net, const float* patches, int n, int group, const int* count, float* a, float* b, float** feat,
+                     cudaStream_t st) {
+    if (net->engine == AG_ENGINE_TC) {
+        // the workspace [a, a + 2*(b-a)) is re-carved as [bufA | bufB | fp32 features]
+        char* base = (char*)a;
+        const size_t total = 2 * (size_t)((char*)b - (char*)a);
+        const size_t act = align_up((size_t)n * tc_act_bytes(net->kind), 256);
+        const size_t fbytes = (size_t)n * (net->kind == AG_NET_HARDNET ? 128 : 64) * 64 * sizeof(float);
+        if (2 * act + fbytes > total) { set_error("tensor-core workspace too small"); return AG_ERR_CAPACITY; }
+        void* bufA = base;
+        void* bufB = base + act;
+        b = (float*)(base + 2 * act);
+        *feat = b;
+        return net->kind == AG_NET_HARDNET ? tc_trunk_hardnet(net, patches, n, group, count, bufA, bufB, b, st)
+                                           : tc_trunk_affnet(net, patches, n, group, count, bufA, bufB, b, st);
+    }
+    *feat = b;
+    return net->kind == AG_NET_HARDNET ? trunk_hardnet(net, patches, n, group, count, a, b, st)
+                                       : trunk_affnet(net, patches, n, group, count, a, b, st);
+}
+
 static int split_ws(int kind, int n, void* d_ws, size_t ws_bytes, float** a, float** b) {
     const size_t need = ag_net_workspace_bytes(kind, n);
     if (d_ws == nullptr || ws_bytes < need) {
@@ -428,7 +477,7 @@ int ag_affnet_forward(const ag_net_t* net, const float* d_patches, int n, const 
     int rc = split_ws(net->kind, n, d_ws, ws_bytes, &a, &b);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = trunk_affnet(net, d_patches, n, group, d_count, a, b, st))) return rc;
+    if ((rc = run_trunk(net, d_patches, n, group, d_count, a, b, &b, st))) return rc;
     affnet_head_kernel<<<cdiv(n, 8), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, n, group, d_count);
     AG_CHECK_LAUNCH("affnet_head_kernel");
     return AG_OK;
@@ -444,7 +493,7 @@ int ag_orinet_forward(const ag_net_t* net, const float* d_patches, int n, const 
     int rc = split_ws(net->kind, n, d_ws, ws_bytes, &a, &b);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = trunk_affnet(net, d_patches, n, group, d_count, a, b, st))) return rc;
+    if ((rc = run_trunk(net, d_patches, n, group, d_count, a, b, &b, st))) return rc;
     orinet_head_kernel<<<cdiv(n, 8), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, d_angle, n, group, d_count);
     AG_CHECK_LAUNCH("orinet_head_kernel");
     return AG_OK;
@@ -460,7 +509,7 @@ int ag_hardnet_forward(const ag_net_t* net, const float* d_patches, int n, const
     int rc = split_ws(net->kind, n, d_ws, ws_bytes, &a, &b);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = trunk_hardnet(net, d_patches, n, group, d_count, a, b, st))) return rc;
+    if ((rc = run_trunk(net, d_patches, n, group, d_count, a, b, &b, st))) return rc;
     hardnet_head_kernel<<<cdiv(n, HH_P), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, n, group, d_count);
     AG_CHECK_LAUNCH("hardnet_head_kernel");
     return AG_OK;

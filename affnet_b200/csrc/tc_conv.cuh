@@ -1,0 +1,308 @@
+// Tensor-core (tcgen05) 3x3 convolution engine for the AffNet / OriNet / HardNet trunks (sm_100a).
+//
+// Formulation: shifted-window implicit GEMM.  The fp16 activations of one patch live in the UMMA canonical
+// no-swizzle K-major layout  [C/8][NPIX][8]  (8 channels = one 16-byte core-matrix row, pixel slots contiguous),
+// over a zero-padded pixel plane.  For tap (dy,dx) the A operand of the M=128 tile starting at output row m0 is
+// the SAME buffer with its descriptor start address advanced by (m0 + off(dy,dx)) * 16 bytes - no im2col copy.
+// Stride-2 layers read a phase-split plane (4 parity planes) so that they are shifted-window GEMMs too.
+//   D[128 x N] (fp32, TMEM) += A[128 x 16] (smem desc) * W[N x 16]^T (smem desc)      9 * C/16 MMAs per tile
+// One persistent CTA keeps the layer's (BatchNorm-folded) weights resident in shared memory and loops over patches:
+//   warp 0   : producer  - one cp.async.bulk per patch (global -> smem stage), mbarrier complete_tx
+//   warp 1   : MMA issuer (single thread) + TMEM allocator
+//   warps 2-5: epilogue  - tcgen05.ld 32x32b, bias + ReLU, fp16 pack, 16-byte stores straight into the NEXT layer's
+//              canonical layout (or fp32 NCHW for the last trunk layer), plus the zero border of that layout.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace ag {
+namespace tc {
+
+enum LayoutKind { PLAIN = 0, PHASE = 1, FINAL = 2 };
+
+// Pixel-slot geometry of an activation buffer that is the INPUT of a layer with `stride` on an HxH map.
+template <int H, int STRIDE>
+struct InLay {
+    static constexpr int HOUT = H / STRIDE;
+    static constexpr int PITCH = (STRIDE == 1) ? H + 2 : H / 2 + 1;          // row pitch of the output-row index space
+    static constexpr int ROWS = (HOUT - 1) * PITCH + HOUT;                    // output rows m = y*PITCH + x
+    static constexpr int TILES = (ROWS + 127) / 128;
+    static constexpr int PLANE = (STRIDE == 1) ? 0 : ((PITCH * PITCH + 7) / 8) * 8;   // parity-plane stride (slots)
+    static constexpr int MAXOFF = (STRIDE == 1) ? 2 * PITCH + 2 : 3 * PLANE + PITCH + 1;
+    static constexpr int NPIX = ((128 * TILES + MAXOFF + 1 + 7) / 8) * 8;     // slots per channel group incl. slack
+    __host__ __device__ static constexpr int tap_off(int dy, int dx) {
+        return (STRIDE == 1) ? dy * PITCH + dx : ((dy & 1) * 2 + (dx & 1)) * PLANE + (dy >> 1) * PITCH + (dx >> 1);
+    }
+    // slot of padded coordinate (Y,X) in [0,H+1]^2
+    __host__ __device__ static constexpr int slot(int Y, int X) {
+        return (STRIDE == 1) ? Y * PITCH + X : ((Y & 1) * 2 + (X & 1)) * PLANE + (Y >> 1) * PITCH + (X >> 1);
+    }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// no-swizzle K-major UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred P;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n @P bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct ConvArgs {
+    const __half* in;     // [n][CIN/8][NPIX_IN][8]
+    void* out;            // next layer's canonical fp16 buffer, or fp32 [n][COUT][HOUT][HOUT]
+    const __half* wpk;    // [NSPLIT][9][CIN/8][COUT/NSPLIT][8]
+    const float* bias;    // [COUT]
+    int n, group;
+    const int* count;
+};
+
+// CIN, COUT: channels; H: input map edge; STRIDE 1|2; NSPLIT: CTAs sharing one patch along COUT; STAGES: smem stages;
+// OUT: layout of the output buffer (PLAIN / PHASE for the next conv, FINAL = fp32 NCHW).
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT>
+struct ConvCfg {
+    using In = InLay<H, STRIDE>;
+    static constexpr int HOUT = H / STRIDE;
+    static constexpr int KC = CIN / 8;                  // 16-byte channel groups
+    static constexpr int NT = COUT / NSPLIT;            // MMA N
+    static constexpr int NACC = 2;                      // TMEM accumulator buffers
+    static constexpr int TMEM_COLS = (NACC * NT <= 32) ? 32 : (NACC * NT <= 64) ? 64 : (NACC * NT <= 128) ? 128 : (NACC * NT <= 256) ? 256 : 512;
+    static constexpr uint32_t IN_BYTES = (uint32_t)KC * In::NPIX * 16;     // one patch
+    static constexpr uint32_t W_BYTES = 9u * KC * NT * 16;
+    static constexpr size_t SMEM = 1024 + (size_t)W_BYTES + (size_t)STAGES * IN_BYTES;
+    // output buffer geometry
+    using OutP = InLay<HOUT, 1>;   // if the consumer has stride 1
+    using OutS = InLay<HOUT, 2>;   // if the consumer has stride 2
+    static constexpr int OUT_NPIX = (OUT == PLAIN) ? OutP::NPIX : (OUT == PHASE) ? OutS::NPIX : 0;
+    static constexpr size_t OUT_BYTES = (OUT == FINAL) ? (size_t)COUT * HOUT * HOUT * 4 : (size_t)(COUT / 8) * OUT_NPIX * 16;
+    static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT <= 256, "UMMA shape");
+    static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT>
+__global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
+    using Cfg = ConvCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT>;
+    using In = typename Cfg::In;
+    constexpr int KC = Cfg::KC, NT = Cfg::NT, NACC = Cfg::NACC, TILES = In::TILES, HOUT = Cfg::HOUT;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [STAGES]
+    uint64_t* empty = full + STAGES;                       // [STAGES]
+    uint64_t* tfull = empty + STAGES;                      // [NACC]
+    uint64_t* tempty = tfull + NACC;                       // [NACC]
+    uint64_t* wbar = tempty + NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    unsigned char* sW = smem + 1024;
+    unsigned char* sIn = sW + Cfg::W_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < NACC; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    auto valid = [&](int pi) -> bool { return a.count == nullptr || (pi % a.group) < a.count[pi / a.group]; };
+
+    if (warp == 0) {
+        // ===== producer =====
+        if (lane == 0) {
+            mbar_expect_tx(wbar, Cfg::W_BYTES);
+            bulk_g2s(sW, reinterpret_cast<const unsigned char*>(a.wpk) + (size_t)split * Cfg::W_BYTES, Cfg::W_BYTES, wbar);
+            int it = 0;
+            for (int pi = blockIdx.x; pi < a.n; pi += gridDim.x) {
+                if (!valid(pi)) continue;
+                const int s = it % STAGES;
+                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], Cfg::IN_BYTES);
+                bulk_g2s(sIn + (size_t)s * Cfg::IN_BYTES, reinterpret_cast<const unsigned char*>(a.in) + (size_t)pi * Cfg::IN_BYTES, Cfg::IN_BYTES,
+                         &full[s]);
+                it++;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            mbar_wait(wbar, 0);
+            tc_fence_after();
+            const uint32_t w_base = smem_u32(sW);
+            int it = 0, tcnt = 0;
+            for (int pi = blockIdx.x; pi < a.n; pi += gridDim.x) {
+                if (!valid(pi)) continue;
+                const int s = it % STAGES;
+                mbar_wait(&full[s], (it / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t in_base = smem_u32(sIn + (size_t)s * Cfg::IN_BYTES);
+#pragma unroll 1
+                for (int t = 0; t < TILES; t++, tcnt++) {
+                    const int ab = tcnt % NACC;
+                    mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem + (uint32_t)(ab * NT);
+#pragma unroll
+                    for (int tap = 0; tap < 9; tap++) {
+                        const uint32_t a_tap = in_base + (uint32_t)(t * 128 + In::tap_off(tap / 3, tap % 3)) * 16u;
+#pragma unroll
+                        for (int j = 0; j < KC / 2; j++) {
+                            const uint64_t da = make_desc(a_tap + (uint32_t)(2 * j) * In::NPIX * 16u, In::NPIX * 16u, 128u);
+                            const uint64_t db = make_desc(w_base + (uint32_t)((tap * KC + 2 * j) * NT) * 16u, NT * 16u, 128u);
+                            umma_f16(d_tmem, da, db, idesc, (tap | j) != 0);
+                        }
+                    }
+                    umma_commit(&tfull[ab]);
+                }
+                umma_commit(&empty[s]);  // all MMAs reading this stage have completed when this arrives
+                it++;
+            }
+        }
+    } else {
+        // ===== epilogue (warps 2..5 -> TMEM lane quadrant warp%4) =====
+        const int q = warp & 3;
+        const int et = (warp - 2) * 32 + lane;  // 0..127
+        int tcnt = 0;
+        for (int pi = blockIdx.x; pi < a.n; pi += gridDim.x) {
+            if (!valid(pi)) continue;
+            unsigned char* outp = reinterpret_cast<unsigned char*>(a.out) + (size_t)pi * Cfg::OUT_BYTES;
+            // zero border of the consumer's padded plane (only by the split that owns channel group range start)
+            if (OUT != FINAL) {
+                constexpr int HB = HOUT + 1;  // border cells: 4*HB
+                for (int i = et; i < 4 * HB; i += 128) {
+                    const int side = i / HB, k = i - side * HB;
+                    int Y, X;
+                    if (side == 0) { Y = 0; X = k; } else if (side == 1) { Y = HOUT + 1; X = k + 1; }
+                    else if (side == 2) { Y = k + 1; X = 0; } else { Y = k; X = HOUT + 1; }
+                    const int slot = (OUT == PLAIN) ? Cfg::OutP::slot(Y, X) : Cfg::OutS::slot(Y, X);
+#pragma unroll
+                    for (int g = 0; g < NT / 8; g++) {
+                        const int cg = split * (NT / 8) + g;
+                        *reinterpret_cast<uint4*>(outp + ((size_t)cg * Cfg::OUT_NPIX + slot) * 16) = make_uint4(0, 0, 0, 0);
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int t = 0; t < TILES; t++, tcnt++) {
+                const int ab = tcnt % NACC;
+                mbar_wait(&tfull[ab], (tcnt / NACC) & 1);
+                tc_fence_after();
+                const int m = t * 128 + q * 32 + lane;
+                const int y = m / In::PITCH, x = m - y * In::PITCH;
+                const bool ok = (y < HOUT) && (x < HOUT);
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NT);
+#pragma unroll
+                for (int c0 = 0; c0 < NT; c0 += 32) {
+                    uint32_t r[32];
+                    if (NT - c0 >= 32) {
+                        tmem_ld32(taddr + c0, r);
+                    } else {
+                        uint32_t r16[16];
+                        tmem_ld16(taddr + c0, r16);
+#pragma unroll
+                        for (int i = 0; i < 16; i++) { r[i] = r16[i]; r[16 + i] = 0; }
+                    }
+                    tmem_ld_wait();
+                    if (c0 + 32 >= NT) {  // last column chunk read: release the accumulator buffer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[ab]);
+                    }
+                    if (ok) {
+                        constexpr int NC = (NT < 32) ? NT : 32;
+#pragma unroll
+                        for (int g = 0; g < NC / 8; g++) {
+                            const int ch = split * NT + c0 + g * 8;
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e++) v[e] = fmaxf(__uint_as_float(r[g * 8 + e]) + __ldg(a.bias + ch + e), 0.f);
+                            if (OUT == FINAL) {
+                                float* o = reinterpret_cast<float*>(outp);
+#pragma unroll
+                                for (int e = 0; e < 8; e++) o[(size_t)(ch + e) * HOUT * HOUT + y * HOUT + x] = v[e];
+                            } else {
+                                const int slot = (OUT == PLAIN) ? Cfg::OutP::slot(y + 1, x + 1) : Cfg::OutS::slot(y + 1, x + 1);
+                                uint4 pk;
+                                pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
+                                *reinterpret_cast<uint4*>(outp + ((size_t)(ch / 8) * Cfg::OUT_NPIX + slot) * 16) = pk;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS));
+    }
+}
+
+}  // namespace tc
+}  // namespace ag

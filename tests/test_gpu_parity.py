@@ -199,21 +199,37 @@ def test_level_selection_identical(L):
     assert torch.equal(o.cpu().float(), oo) and torch.equal(l.cpu().float(), lo)
 
 
-def test_nets_vs_oracle(L, nets):
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+def test_nets_vs_oracle(L, nets, engine):
+    """a9/a12/a16.  simt = exact fp32 engine (1e-4); tc = tcgen05 engine, fp16 operands + fp32 accumulate with fp32 first
+    layer and head: north_star's 1e-3 for HardNet descriptors; AffNet/OriNet on tc are reported (they default to simt)."""
     aff, ori, hn = nets
+    e = L.ENGINE_SIMT if engine == "simt" else L.ENGINE_TC
     z = gold("graf_crop.npz")
     g = torch.Generator().manual_seed(8)
     sets = [torch.from_numpy(z["aff_patches"]), torch.from_numpy(z["ori_desc_patches"]), torch.rand(37, 1, 32, 32, generator=g) * 255,
-            torch.from_numpy(gold("face_patches.npz")["patches_u8"].astype(np.float32) / 255.0).view(-1, 1, 32, 32)]
-    for P in sets:
-        Pd = P.to(DEV)
-        dA = (aff(Pd).cpu() - O.affnet_forward(P, W["affnet"])).abs().max().item()
-        dR = (ori(Pd).cpu() - O.orinet_forward(P, W["orinet"])).abs().max().item()
-        dang = (ori(Pd, return_rot_matrix=False).cpu() - O.orinet_angle(P, W["orinet"]))
-        dang = torch.atan2(torch.sin(dang), torch.cos(dang)).abs().max().item()
-        dD = (hn(Pd).cpu() - O.hardnet_forward(P, W["hardnet"])).abs().max().item()
-        assert dA < 1e-3 and dR < 1e-3 and dang < 1e-3 and dD < 1e-3, (dA, dR, dang, dD)   # north_star: 1e-3 fp32
-        assert dA < 1e-4 and dD < 1e-4, (dA, dD)                                           # fp32 SIMT engine is much tighter
+            torch.from_numpy(gold("face_patches.npz")["patches_u8"].astype(np.float32) / 255.0).view(-1, 1, 32, 32),
+            torch.rand(300, 1, 32, 32, generator=g)]
+    try:
+        for m in (aff, ori, hn):
+            m.set_engine(e)
+        worst = [0.0, 0.0, 0.0, 0.0]
+        for P in sets:
+            Pd = P.to(DEV)
+            dA = (aff(Pd).cpu() - O.affnet_forward(P, W["affnet"])).abs().max().item()
+            dR = (ori(Pd).cpu() - O.orinet_forward(P, W["orinet"])).abs().max().item()
+            dang = (ori(Pd, return_rot_matrix=False).cpu() - O.orinet_angle(P, W["orinet"]))
+            dang = torch.atan2(torch.sin(dang), torch.cos(dang)).abs().max().item()
+            dD = (hn(Pd).cpu() - O.hardnet_forward(P, W["hardnet"])).abs().max().item()
+            worst = [max(a, b) for a, b in zip(worst, (dA, dR, dang, dD))]
+        print("\nengine %s: max|dA| %.2e  max|dR| %.2e  max|dangle| %.2e rad  max|ddesc| %.2e" % ((engine,) + tuple(worst)))
+        if engine == "simt":
+            assert max(worst) < 1e-4, worst
+        else:
+            assert worst[3] < 1e-3, worst                       # HardNet descriptors within 1e-3 on tensor cores
+            assert worst[0] < 1e-2 and worst[2] < 1e-2, worst   # single-pass fp16 AffNet/OriNet: sanity bound only
+    finally:
+        aff.set_engine(L.ENGINE_SIMT); ori.set_engine(L.ENGINE_SIMT); hn.set_engine(L.ENGINE_TC)
     assert aff(torch.empty(0, 1, 32, 32, device=DEV)).shape == (0, 2, 2)
 
 
