@@ -14,7 +14,7 @@ struct ag_net {
     float* d_w[6];     // fp32 [9][cin][cout], BN folded   (d_w[0] doubles as the [9][C] first-layer weights)
     float* d_b[6];     // fp32 [cout]  (BN shift)
     float* d_w1;       // == d_w[0]
-    __half* d_wh[6];   // fp16 [nsplit][9][cin/8][cout/nsplit][8] for layers 1..5 (index 0 unused)
+    __half* d_wh[6];   // fp16 [nsplit][hi|lo][9][cin/8][cout/nsplit][8] for layers 1..5 (index 0 unused; lo only for AffNet/OriNet)
     float* d_head_w;   // AffNet [3][4096], OriNet [2][4096], HardNet [8192][128]
     float* d_head_b;   // AffNet bias[3], OriNet bias[2], HardNet {scale[128], shift[128]}
     float* d_all;      // fp32 allocation
@@ -24,8 +24,11 @@ struct ag_net {
 namespace ag {
 size_t tc_act_bytes(int kind);
 int tc_nsplit(int kind, int layer);
+int tc_split_w(int kind);
 int tc_trunk_hardnet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
                      cudaStream_t st);
+int tc_trunk_orinet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
+                    cudaStream_t st);
 int tc_trunk_affnet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
                     cudaStream_t st);
 }  // namespace ag

@@ -340,27 +340,32 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
         packed.insert(packed.end(), bias, bias + no);
         while (packed.size() % 4) packed.push_back(0.f);
     }
-    // fp16 packs for the tensor-core engine: [nsplit][9][cin/8][cout/nsplit][8], layers 1..5
+    // fp16 packs for the tensor-core engine: [nsplit][hi|lo][9][cin/8][cout/nsplit][8], layers 1..5
     std::vector<__half> packed_h;
     size_t wh_off[6] = {0, 0, 0, 0, 0, 0};
+    const int sw = tc_split_w(kind);
     for (int l = 1; l < 6; l++) {
         const int ci = cfg[l].cin, co = cfg[l].cout, ns = tc_nsplit(kind, l), nt = co / ns, kc = ci / 8;
         const float* wf = packed.data() + w_off[l];  // [tap][ci][co]
         wh_off[l] = packed_h.size();
-        packed_h.resize(packed_h.size() + (size_t)9 * ci * co);
+        packed_h.resize(packed_h.size() + (size_t)9 * ci * co * (1 + sw));
         __half* dst = packed_h.data() + wh_off[l];
         for (int sp = 0; sp < ns; sp++)
-            for (int tap = 0; tap < 9; tap++)
-                for (int g = 0; g < kc; g++)
-                    for (int nn = 0; nn < nt; nn++)
-                        for (int e = 0; e < 8; e++)
-                            dst[((((size_t)sp * 9 + tap) * kc + g) * nt + nn) * 8 + e] =
-                                __float2half_rn(wf[((size_t)tap * ci + g * 8 + e) * co + sp * nt + nn]);
+            for (int part = 0; part <= sw; part++)
+                for (int tap = 0; tap < 9; tap++)
+                    for (int g = 0; g < kc; g++)
+                        for (int nn = 0; nn < nt; nn++)
+                            for (int e = 0; e < 8; e++) {
+                                const float v = wf[((size_t)tap * ci + g * 8 + e) * co + sp * nt + nn];
+                                const __half hi = __float2half_rn(v);
+                                const __half val = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
+                                dst[(((((size_t)sp * (1 + sw) + part) * 9 + tap) * kc + g) * nt + nn) * 8 + e] = val;
+                            }
     }
     ag_net* net = new ag_net();
     memset(net, 0, sizeof(*net));
     net->kind = kind;
-    net->engine = (kind == AG_NET_HARDNET) ? AG_ENGINE_TC : AG_ENGINE_SIMT;
+    net->engine = AG_ENGINE_TC;
     {
         int rch = check_cuda(cudaMalloc(&net->d_all_h, packed_h.size() * sizeof(__half)), "cudaMalloc fp16 weights");
         if (rch != AG_OK) { delete net; return rch; }
@@ -398,8 +403,11 @@ int ag_net_get_engine(const ag_net_t* net) { return net ? net->engine : -1; }
 
 size_t ag_net_workspace_bytes(int kind, int n) {
     if (n <= 0) return 0;
-    const size_t per = (kind == AG_NET_HARDNET) ? 32768 : 16384;  // largest activation per patch (floats)
-    return 2 * align_up((size_t)n * per * sizeof(float), 256);
+    const size_t per = (kind == AG_NET_HARDNET) ? 32768 : 16384;  // largest fp32 activation per patch (floats), SIMT engine
+    const size_t simt = 2 * align_up((size_t)n * per * sizeof(float), 256);
+    const size_t tcb = 2 * align_up((size_t)n * tc_act_bytes(kind), 256) +
+                       align_up((size_t)n * (kind == AG_NET_HARDNET ? 128 : 64) * 64 * sizeof(float), 256);
+    return simt > tcb ? simt : tcb;
 }
 
 }  // extern "C"
@@ -444,8 +452,9 @@ static int run_trunk(const ag_net* net, const float* patches, int n, int group, 
         void* bufB = base + act;
         b = (float*)(base + 2 * act);
         *feat = b;
-        return net->kind == AG_NET_HARDNET ? tc_trunk_hardnet(net, patches, n, group, count, bufA, bufB, b, st)
-                                           : tc_trunk_affnet(net, patches, n, group, count, bufA, bufB, b, st);
+        if (net->kind == AG_NET_HARDNET) return tc_trunk_hardnet(net, patches, n, group, count, bufA, bufB, b, st);
+        if (net->kind == AG_NET_ORINET) return tc_trunk_orinet(net, patches, n, group, count, bufA, bufB, b, st);
+        return tc_trunk_affnet(net, patches, n, group, count, bufA, bufB, b, st);
     }
     *feat = b;
     return net->kind == AG_NET_HARDNET ? trunk_hardnet(net, patches, n, group, count, a, b, st)

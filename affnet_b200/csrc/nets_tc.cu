@@ -11,7 +11,7 @@ namespace ag {
 namespace tc {
 
 // ---- layer 1: input_norm + conv3x3(1 -> C) + ReLU -> fp16 PLAIN(32) ------------------------------------------------
-template <int C>
+template <int C, int OSA>
 __global__ void __launch_bounds__(256) first_layer_kernel(const float* __restrict__ patches, __half* __restrict__ out,
                                                           const float* __restrict__ wpk /*[9][C]*/, const float* __restrict__ bias,
                                                           int group, const int* __restrict__ count) {
@@ -51,14 +51,14 @@ __global__ void __launch_bounds__(256) first_layer_kernel(const float* __restric
         s_in[(p >> 5) + 1][(p & 31) + 1] = (v4[k] - mean) * inv;
     }
     __syncthreads();
-    unsigned char* outp = reinterpret_cast<unsigned char*>(out) + (size_t)pi * (C / 8) * Lay::NPIX * 16;
+    unsigned char* outp = reinterpret_cast<unsigned char*>(out) + (size_t)pi * (C / 8) * (1 + OSA) * Lay::NPIX * 16;
     // zero border of the padded plane
     for (int i = threadIdx.x; i < 4 * 33; i += 256) {
         const int side = i / 33, k = i - side * 33;
         int Y, X;
         if (side == 0) { Y = 0; X = k; } else if (side == 1) { Y = 33; X = k + 1; } else if (side == 2) { Y = k + 1; X = 0; } else { Y = k; X = 33; }
 #pragma unroll
-        for (int g = 0; g < C / 8; g++) *reinterpret_cast<uint4*>(outp + ((size_t)g * Lay::NPIX + Lay::slot(Y, X)) * 16) = make_uint4(0, 0, 0, 0);
+        for (int g = 0; g < (C / 8) * (1 + OSA); g++) *reinterpret_cast<uint4*>(outp + ((size_t)g * Lay::NPIX + Lay::slot(Y, X)) * 16) = make_uint4(0, 0, 0, 0);
     }
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
@@ -81,6 +81,13 @@ __global__ void __launch_bounds__(256) first_layer_kernel(const float* __restric
             pk.z = pack_h2(fmaxf(acc[g * 8 + 4], 0.f), fmaxf(acc[g * 8 + 5], 0.f));
             pk.w = pack_h2(fmaxf(acc[g * 8 + 6], 0.f), fmaxf(acc[g * 8 + 7], 0.f));
             *reinterpret_cast<uint4*>(outp + ((size_t)g * Lay::NPIX + slot) * 16) = pk;
+            if (OSA) {
+                float l[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) { const float v = fmaxf(acc[g * 8 + e], 0.f); l[e] = v - __half2float(__float2half_rn(v)); }
+                pk.x = pack_h2(l[0], l[1]); pk.y = pack_h2(l[2], l[3]); pk.z = pack_h2(l[4], l[5]); pk.w = pack_h2(l[6], l[7]);
+                *reinterpret_cast<uint4*>(outp + ((size_t)(C / 8 + g) * Lay::NPIX + slot) * 16) = pk;
+            }
         }
     }
 }
@@ -96,10 +103,10 @@ static int num_sms() {
     return g_num_sms;
 }
 
-template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT>
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA = 0, int SW = 0, int OSA = 0>
 static int launch_tc(const __half* in, void* out, const __half* w, const float* b, int n, int group, const int* count, cudaStream_t st) {
-    using Cfg = ConvCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT>;
-    auto kern = tc_conv_kernel<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT>;
+    using Cfg = ConvCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA>;
+    auto kern = tc_conv_kernel<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA>;
     static bool configured = false;
     if (!configured) {
         int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM), "tc_conv smem attr");
@@ -118,20 +125,21 @@ static int launch_tc(const __half* in, void* out, const __half* w, const float* 
 
 }  // namespace tc
 
-// bytes per patch of the two ping-pong fp16 activation buffers
+// bytes per patch of each of the two ping-pong fp16 activation buffers (largest layer output)
 size_t tc_act_bytes(int kind) {
     using namespace tc;
-    if (kind == AG_NET_HARDNET) return ConvCfg<32, 32, 32, 1, 1, 2, PHASE>::OUT_BYTES;  // 82,944 B: largest buffer (L2 out)
-    return ConvCfg<16, 16, 32, 1, 1, 2, PHASE>::OUT_BYTES;
+    if (kind == AG_NET_HARDNET) return ConvCfg<32, 32, 32, 1, 1, 2, PHASE>::OUT_BYTES;        // 82,944 B (L2 out)
+    if (kind == AG_NET_ORINET) return ConvCfg<16, 16, 32, 1, 1, 2, PHASE, 1, 1, 1>::OUT_BYTES;  // hi+lo planes
+    return ConvCfg<16, 16, 32, 1, 1, 2, PHASE, 0, 1, 0>::OUT_BYTES;
 }
 
-// HardNet trunk -> fp32 features [n,128,8,8] in `feat`
+// HardNet trunk -> fp32 features [n,128,8,8] in `feat`.  fp16 operands (descriptor error 6e-4 < 1e-3).
 int tc_trunk_hardnet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
                      cudaStream_t st) {
     using namespace tc;
     __half* A = (__half*)bufA;
     __half* B = (__half*)bufB;
-    first_layer_kernel<32><<<n, 256, 0, st>>>(patches, A, net->d_w1, net->d_b[0], group, count);
+    first_layer_kernel<32, 0><<<n, 256, 0, st>>>(patches, A, net->d_w1, net->d_b[0], group, count);
     AG_CHECK_LAUNCH("first_layer_kernel");
     int rc;
     if ((rc = launch_tc<32, 32, 32, 1, 1, 2, PHASE>(A, B, net->d_wh[1], net->d_b[1], n, group, count, st))) return rc;
@@ -142,23 +150,42 @@ int tc_trunk_hardnet(const ag_net* net, const float* patches, int n, int group, 
     return AG_OK;
 }
 
-// AffNet / OriNet trunk (same architecture) -> fp32 features [n,64,8,8]
+// AffNet trunk -> fp32 features [n,64,8,8].  Weights split hi/lo (A error 1.8e-4; plain fp16 weights give 1.8e-3).
 int tc_trunk_affnet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
                     cudaStream_t st) {
     using namespace tc;
     __half* A = (__half*)bufA;
     __half* B = (__half*)bufB;
-    first_layer_kernel<16><<<n, 256, 0, st>>>(patches, A, net->d_w1, net->d_b[0], group, count);
+    first_layer_kernel<16, 0><<<n, 256, 0, st>>>(patches, A, net->d_w1, net->d_b[0], group, count);
     AG_CHECK_LAUNCH("first_layer_kernel");
     int rc;
-    if ((rc = launch_tc<16, 16, 32, 1, 1, 2, PHASE>(A, B, net->d_wh[1], net->d_b[1], n, group, count, st))) return rc;
-    if ((rc = launch_tc<16, 32, 32, 2, 1, 2, PLAIN>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
-    if ((rc = launch_tc<32, 32, 16, 1, 1, 2, PHASE>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
-    if ((rc = launch_tc<32, 64, 16, 2, 1, 2, PLAIN>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
-    if ((rc = launch_tc<64, 64, 8, 1, 1, 2, FINAL>(A, feat, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
+    if ((rc = launch_tc<16, 16, 32, 1, 1, 2, PHASE, 0, 1, 0>(A, B, net->d_wh[1], net->d_b[1], n, group, count, st))) return rc;
+    if ((rc = launch_tc<16, 32, 32, 2, 1, 2, PLAIN, 0, 1, 0>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
+    if ((rc = launch_tc<32, 32, 16, 1, 1, 2, PHASE, 0, 1, 0>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
+    if ((rc = launch_tc<32, 64, 16, 2, 1, 2, PLAIN, 0, 1, 0>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
+    if ((rc = launch_tc<64, 64, 8, 1, 1, 2, FINAL, 0, 1, 0>(A, feat, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
+    return AG_OK;
+}
+
+// OriNet trunk -> fp32 features [n,64,8,8].  The angle is ill-conditioned in the features (fp16 activations give 8e-3 rad),
+// so both operands are split: three MMAs per K step, fp32-grade result (1.6e-5 rad in emulation).
+int tc_trunk_orinet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
+                    cudaStream_t st) {
+    using namespace tc;
+    __half* A = (__half*)bufA;
+    __half* B = (__half*)bufB;
+    first_layer_kernel<16, 1><<<n, 256, 0, st>>>(patches, A, net->d_w1, net->d_b[0], group, count);
+    AG_CHECK_LAUNCH("first_layer_kernel");
+    int rc;
+    if ((rc = launch_tc<16, 16, 32, 1, 1, 2, PHASE, 1, 1, 1>(A, B, net->d_wh[1], net->d_b[1], n, group, count, st))) return rc;
+    if ((rc = launch_tc<16, 32, 32, 2, 1, 2, PLAIN, 1, 1, 1>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
+    if ((rc = launch_tc<32, 32, 16, 1, 1, 2, PHASE, 1, 1, 1>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
+    if ((rc = launch_tc<32, 64, 16, 2, 1, 2, PLAIN, 1, 1, 1>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
+    if ((rc = launch_tc<64, 64, 8, 1, 1, 2, FINAL, 1, 1, 0>(A, feat, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
     return AG_OK;
 }
 
 int tc_nsplit(int kind, int layer) { return (kind == AG_NET_HARDNET && layer >= 4) ? 2 : 1; }
+int tc_split_w(int kind) { return kind == AG_NET_HARDNET ? 0 : 1; }
 
 }  // namespace ag

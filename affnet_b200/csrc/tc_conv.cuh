@@ -107,7 +107,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 struct ConvArgs {
     const __half* in;     // [n][CIN/8][NPIX_IN][8]
     void* out;            // next layer's canonical fp16 buffer, or fp32 [n][COUT][HOUT][HOUT]
-    const __half* wpk;    // [NSPLIT][9][CIN/8][COUT/NSPLIT][8]
+    const __half* wpk;    // [NSPLIT][hi|lo][9][CIN/8][COUT/NSPLIT][8]  (lo block only if SW)
     const float* bias;    // [COUT]
     int n, group;
     const int* count;
@@ -115,7 +115,10 @@ struct ConvArgs {
 
 // CIN, COUT: channels; H: input map edge; STRIDE 1|2; NSPLIT: CTAs sharing one patch along COUT; STAGES: smem stages;
 // OUT: layout of the output buffer (PLAIN / PHASE for the next conv, FINAL = fp32 NCHW).
-template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT>
+// Split precision (fp32-grade results from fp16 tensor cores): SA = the input carries hi and lo fp16 planes
+// (x = hi + lo, channel groups [0,KC) hi then [KC,2KC) lo), SW = the weights carry hi and lo copies, OSA = write the
+// output as hi/lo planes.  D = A_hi W_hi (+ A_lo W_hi if SA) (+ A_hi W_lo if SW); the lo*lo term (2^-22) is dropped.
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA = 0, int SW = 0, int OSA = 0>
 struct ConvCfg {
     using In = InLay<H, STRIDE>;
     static constexpr int HOUT = H / STRIDE;
@@ -123,21 +126,22 @@ struct ConvCfg {
     static constexpr int NT = COUT / NSPLIT;            // MMA N
     static constexpr int NACC = 2;                      // TMEM accumulator buffers
     static constexpr int TMEM_COLS = (NACC * NT <= 32) ? 32 : (NACC * NT <= 64) ? 64 : (NACC * NT <= 128) ? 128 : (NACC * NT <= 256) ? 256 : 512;
-    static constexpr uint32_t IN_BYTES = (uint32_t)KC * In::NPIX * 16;     // one patch
-    static constexpr uint32_t W_BYTES = 9u * KC * NT * 16;
+    static constexpr uint32_t IN_BYTES = (uint32_t)KC * (1 + SA) * In::NPIX * 16;     // one patch
+    static constexpr uint32_t W_HALF = 9u * KC * NT * 16;
+    static constexpr uint32_t W_BYTES = W_HALF * (1 + SW);
     static constexpr size_t SMEM = 1024 + (size_t)W_BYTES + (size_t)STAGES * IN_BYTES;
     // output buffer geometry
     using OutP = InLay<HOUT, 1>;   // if the consumer has stride 1
     using OutS = InLay<HOUT, 2>;   // if the consumer has stride 2
     static constexpr int OUT_NPIX = (OUT == PLAIN) ? OutP::NPIX : (OUT == PHASE) ? OutS::NPIX : 0;
-    static constexpr size_t OUT_BYTES = (OUT == FINAL) ? (size_t)COUT * HOUT * HOUT * 4 : (size_t)(COUT / 8) * OUT_NPIX * 16;
+    static constexpr size_t OUT_BYTES = (OUT == FINAL) ? (size_t)COUT * HOUT * HOUT * 4 : (size_t)(COUT / 8) * (1 + OSA) * OUT_NPIX * 16;
     static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT <= 256, "UMMA shape");
     static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT>
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA>
 __global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
-    using Cfg = ConvCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT>;
+    using Cfg = ConvCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA>;
     using In = typename Cfg::In;
     constexpr int KC = Cfg::KC, NT = Cfg::NT, NACC = Cfg::NACC, TILES = In::TILES, HOUT = Cfg::HOUT;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -214,6 +218,14 @@ __global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
                             const uint64_t da = make_desc(a_tap + (uint32_t)(2 * j) * In::NPIX * 16u, In::NPIX * 16u, 128u);
                             const uint64_t db = make_desc(w_base + (uint32_t)((tap * KC + 2 * j) * NT) * 16u, NT * 16u, 128u);
                             umma_f16(d_tmem, da, db, idesc, (tap | j) != 0);
+                            if (SA) {  // A_lo * W_hi
+                                const uint64_t dal = make_desc(a_tap + (uint32_t)(KC + 2 * j) * In::NPIX * 16u, In::NPIX * 16u, 128u);
+                                umma_f16(d_tmem, dal, db, idesc, 1u);
+                            }
+                            if (SW) {  // A_hi * W_lo
+                                const uint64_t dbl = make_desc(w_base + Cfg::W_HALF + (uint32_t)((tap * KC + 2 * j) * NT) * 16u, NT * 16u, 128u);
+                                umma_f16(d_tmem, da, dbl, idesc, 1u);
+                            }
                         }
                     }
                     umma_commit(&tfull[ab]);
@@ -243,6 +255,7 @@ __global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
                     for (int g = 0; g < NT / 8; g++) {
                         const int cg = split * (NT / 8) + g;
                         *reinterpret_cast<uint4*>(outp + ((size_t)cg * Cfg::OUT_NPIX + slot) * 16) = make_uint4(0, 0, 0, 0);
+                        if (OSA) *reinterpret_cast<uint4*>(outp + ((size_t)(COUT / 8 + cg) * Cfg::OUT_NPIX + slot) * 16) = make_uint4(0, 0, 0, 0);
                     }
                 }
             }
@@ -289,6 +302,13 @@ __global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
                                 uint4 pk;
                                 pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
                                 *reinterpret_cast<uint4*>(outp + ((size_t)(ch / 8) * Cfg::OUT_NPIX + slot) * 16) = pk;
+                                if (OSA) {  // residual plane: lo = fp16(v - fp16(v))
+                                    float l[8];
+#pragma unroll
+                                    for (int e = 0; e < 8; e++) l[e] = v[e] - __half2float(__float2half_rn(v[e]));
+                                    pk.x = pack_h2(l[0], l[1]); pk.y = pack_h2(l[2], l[3]); pk.z = pack_h2(l[4], l[5]); pk.w = pack_h2(l[6], l[7]);
+                                    *reinterpret_cast<uint4*>(outp + ((size_t)(COUT / 8 + ch / 8) * Cfg::OUT_NPIX + slot) * 16) = pk;
+                                }
                             }
                         }
                     }
