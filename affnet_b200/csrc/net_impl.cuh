@@ -15,6 +15,7 @@ struct ag_net {
     float* d_b[6];     // fp32 [cout]  (BN shift)
     float* d_w1;       // == d_w[0]
     __half* d_wh[6];   // fp16 [nsplit][hi|lo][9][cin/8][cout/nsplit][8] for layers 1..5 (index 0 unused; lo only for AffNet/OriNet)
+    __half* d_headh;   // HardNet head for the tensor-core GEMM: fp16 [8192/8][128][8], k = (pixel*16 + c/8)*8 + c%8
     float* d_head_w;   // AffNet [3][4096], OriNet [2][4096], HardNet [8192][128]
     float* d_head_b;   // AffNet bias[3], OriNet bias[2], HardNet {scale[128], shift[128]}
     float* d_all;      // fp32 allocation
@@ -25,8 +26,8 @@ namespace ag {
 size_t tc_act_bytes(int kind);
 int tc_nsplit(int kind, int layer);
 int tc_split_w(int kind);
-int tc_trunk_hardnet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
-                     cudaStream_t st);
+int tc_hardnet_forward(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, void* headbuf,
+                       float* out, cudaStream_t st);
 int tc_trunk_orinet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
                     cudaStream_t st);
 int tc_trunk_affnet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,

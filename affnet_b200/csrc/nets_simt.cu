@@ -362,6 +362,19 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
                                 dst[(((((size_t)sp * (1 + sw) + part) * 9 + tap) * kc + g) * nt + nn) * 8 + e] = val;
                             }
     }
+    size_t headh_off = 0;
+    if (kind == AG_NET_HARDNET) {
+        while (packed_h.size() % 8) packed_h.push_back(__float2half_rn(0.f));
+        headh_off = packed_h.size();
+        packed_h.resize(packed_h.size() + (size_t)8192 * 128);
+        __half* dst = packed_h.data() + headh_off;
+        const float* hw = packed.data() + hw_off;  // [k = c*64 + p][cout]
+        for (int pix = 0; pix < 64; pix++)
+            for (int cg = 0; cg < 16; cg++)
+                for (int o = 0; o < 128; o++)
+                    for (int e = 0; e < 8; e++)
+                        dst[(((size_t)(pix * 16 + cg)) * 128 + o) * 8 + e] = __float2half_rn(hw[((size_t)(cg * 8 + e) * 64 + pix) * 128 + o]);
+    }
     ag_net* net = new ag_net();
     memset(net, 0, sizeof(*net));
     net->kind = kind;
@@ -372,6 +385,7 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
         rch = check_cuda(cudaMemcpy(net->d_all_h, packed_h.data(), packed_h.size() * sizeof(__half), cudaMemcpyHostToDevice), "upload fp16 weights");
         if (rch != AG_OK) { cudaFree(net->d_all_h); delete net; return rch; }
         for (int l = 1; l < 6; l++) net->d_wh[l] = net->d_all_h + wh_off[l];
+        if (kind == AG_NET_HARDNET) net->d_headh = net->d_all_h + headh_off;
     }
     int rc = check_cuda(cudaMalloc(&net->d_all, packed.size() * sizeof(float)), "cudaMalloc weights");
     if (rc != AG_OK) { cudaFree(net->d_all_h); delete net; return rc; }
@@ -405,8 +419,10 @@ size_t ag_net_workspace_bytes(int kind, int n) {
     if (n <= 0) return 0;
     const size_t per = (kind == AG_NET_HARDNET) ? 32768 : 16384;  // largest fp32 activation per patch (floats), SIMT engine
     const size_t simt = 2 * align_up((size_t)n * per * sizeof(float), 256);
+    // tensor-core engine: two fp16 ping-pong buffers + fp32 features (AffNet/OriNet) or the fp16 head operand (HardNet, padded
+    // to a multiple of 128 patches)
     const size_t tcb = 2 * align_up((size_t)n * tc_act_bytes(kind), 256) +
-                       align_up((size_t)n * (kind == AG_NET_HARDNET ? 128 : 64) * 64 * sizeof(float), 256);
+                       (kind == AG_NET_HARDNET ? align_up(((size_t)n + 128) * 8192 * 2, 256) : align_up((size_t)n * 64 * 64 * sizeof(float), 256));
     return simt > tcb ? simt : tcb;
 }
 
@@ -446,13 +462,13 @@ static int run_trunk(const ag_net* net, const float* patches, int n, int group, 
         char* base = (char*)a;
         const size_t total = 2 * (size_t)((char*)b - (char*)a);
         const size_t act = align_up((size_t)n * tc_act_bytes(net->kind), 256);
-        const size_t fbytes = (size_t)n * (net->kind == AG_NET_HARDNET ? 128 : 64) * 64 * sizeof(float);
+        const size_t fbytes = (size_t)n * 64 * 64 * sizeof(float);
         if (2 * act + fbytes > total) { set_error("tensor-core workspace too small"); return AG_ERR_CAPACITY; }
         void* bufA = base;
         void* bufB = base + act;
         b = (float*)(base + 2 * act);
         *feat = b;
-        if (net->kind == AG_NET_HARDNET) return tc_trunk_hardnet(net, patches, n, group, count, bufA, bufB, b, st);
+        if (net->kind == AG_NET_HARDNET) { set_error("HardNet tensor-core path has its own entry"); return AG_ERR_INVALID; }
         if (net->kind == AG_NET_ORINET) return tc_trunk_orinet(net, patches, n, group, count, bufA, bufB, b, st);
         return tc_trunk_affnet(net, patches, n, group, count, bufA, bufB, b, st);
     }
@@ -518,6 +534,11 @@ int ag_hardnet_forward(const ag_net_t* net, const float* d_patches, int n, const
     int rc = split_ws(net->kind, n, d_ws, ws_bytes, &a, &b);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (net->engine == AG_ENGINE_TC) {
+        char* base = (char*)d_ws;
+        const size_t act = align_up((size_t)n * tc_act_bytes(net->kind), 256);
+        return tc_hardnet_forward(net, d_patches, n, group, d_count, base, base + act, base + 2 * act, d_out, st);
+    }
     if ((rc = run_trunk(net, d_patches, n, group, d_count, a, b, &b, st))) return rc;
     hardnet_head_kernel<<<cdiv(n, HH_P), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, n, group, d_count);
     AG_CHECK_LAUNCH("hardnet_head_kernel");

@@ -6,6 +6,7 @@
 
 #include "net_impl.cuh"
 #include "tc_conv.cuh"
+#include "tc_head.cuh"
 
 namespace ag {
 namespace tc {
@@ -133,9 +134,10 @@ size_t tc_act_bytes(int kind) {
     return ConvCfg<16, 16, 32, 1, 1, 2, PHASE, 0, 1, 0>::OUT_BYTES;
 }
 
-// HardNet trunk -> fp32 features [n,128,8,8] in `feat`.  fp16 operands (descriptor error 6e-4 < 1e-3).
-int tc_trunk_hardnet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
-                     cudaStream_t st) {
+// HardNet: trunk (fp16 operands) + tensor-core head -> L2-normalised descriptors [n,128] in `out`.
+// `headbuf` holds the last layer's output in the HEADL layout for ceil(n/128)*128 patches (16 KiB each).
+int tc_hardnet_forward(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, void* headbuf,
+                       float* out, cudaStream_t st) {
     using namespace tc;
     __half* A = (__half*)bufA;
     __half* B = (__half*)bufB;
@@ -146,7 +148,15 @@ int tc_trunk_hardnet(const ag_net* net, const float* patches, int n, int group, 
     if ((rc = launch_tc<32, 64, 32, 2, 1, 2, PLAIN>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
     if ((rc = launch_tc<64, 64, 16, 1, 1, 2, PHASE>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
     if ((rc = launch_tc<64, 128, 16, 2, 2, 2, PLAIN>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
-    if ((rc = launch_tc<128, 128, 8, 1, 2, 2, FINAL>(A, feat, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
+    if ((rc = launch_tc<128, 128, 8, 1, 2, 2, HEADL>(A, headbuf, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        rc = check_cuda(cudaFuncSetAttribute(tc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM), "tc_head smem attr");
+        if (rc != AG_OK) return rc;
+        configured = true;
+    }
+    tc_head_kernel<<<(n + 127) / 128, 192, HEAD_SMEM, st>>>((const __half*)headbuf, net->d_headh, net->d_head_b, out, n, group, count);
+    AG_CHECK_LAUNCH("tc_head_kernel");
     return AG_OK;
 }
 

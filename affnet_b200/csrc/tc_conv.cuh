@@ -19,7 +19,7 @@
 namespace ag {
 namespace tc {
 
-enum LayoutKind { PLAIN = 0, PHASE = 1, FINAL = 2 };
+enum LayoutKind { PLAIN = 0, PHASE = 1, FINAL = 2, HEADL = 3 };  // HEADL: fp16 [patch/128][pixel*C/8 + c/8][patch%128][8], the A operand of the 8x8-head GEMM
 
 // Pixel-slot geometry of an activation buffer that is the INPUT of a layer with `stride` on an HxH map.
 template <int H, int STRIDE>
@@ -134,7 +134,9 @@ struct ConvCfg {
     using OutP = InLay<HOUT, 1>;   // if the consumer has stride 1
     using OutS = InLay<HOUT, 2>;   // if the consumer has stride 2
     static constexpr int OUT_NPIX = (OUT == PLAIN) ? OutP::NPIX : (OUT == PHASE) ? OutS::NPIX : 0;
-    static constexpr size_t OUT_BYTES = (OUT == FINAL) ? (size_t)COUT * HOUT * HOUT * 4 : (size_t)(COUT / 8) * (1 + OSA) * OUT_NPIX * 16;
+    static constexpr size_t OUT_BYTES = (OUT == FINAL) ? (size_t)COUT * HOUT * HOUT * 4
+                                        : (OUT == HEADL) ? (size_t)COUT * HOUT * HOUT * 2
+                                                         : (size_t)(COUT / 8) * (1 + OSA) * OUT_NPIX * 16;
     static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT <= 256, "UMMA shape");
     static_assert(SMEM <= 232448, "shared memory budget");
 };
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
             if (!valid(pi)) continue;
             unsigned char* outp = reinterpret_cast<unsigned char*>(a.out) + (size_t)pi * Cfg::OUT_BYTES;
             // zero border of the consumer's padded plane (only by the split that owns channel group range start)
-            if (OUT != FINAL) {
+            if (OUT == PLAIN || OUT == PHASE) {
                 constexpr int HB = HOUT + 1;  // border cells: 4*HB
                 for (int i = et; i < 4 * HB; i += 128) {
                     const int side = i / HB, k = i - side * HB;
@@ -297,6 +299,12 @@ __global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
                                 float* o = reinterpret_cast<float*>(outp);
 #pragma unroll
                                 for (int e = 0; e < 8; e++) o[(size_t)(ch + e) * HOUT * HOUT + y * HOUT + x] = v[e];
+                            } else if (OUT == HEADL) {
+                                uint4 pk;
+                                pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
+                                const size_t kch = (size_t)(y * HOUT + x) * (COUT / 8) + ch / 8;
+                                unsigned char* hb = reinterpret_cast<unsigned char*>(a.out);
+                                *reinterpret_cast<uint4*>(hb + (((size_t)(pi >> 7) * (HOUT * HOUT * COUT / 8) + kch) * 128 + (pi & 127)) * 16) = pk;
                             } else {
                                 const int slot = (OUT == PLAIN) ? Cfg::OutP::slot(y + 1, x + 1) : Cfg::OutS::slot(y + 1, x + 1);
                                 uint4 pk;

@@ -253,33 +253,47 @@ def main():
     # ---- per-kernel CUDA-event profile of the same step (non-graph launch path), rank 0 ---------------------------
     roof = None
     if rank == 0:
-        per_kernel = {}
+        per_kernel, order = {}, []
         prof_steps = 3
-        for _ in range(prof_steps):
+        for i in range(prof_steps):
             flush.fill_(1.0)
-            for name, ms in L.profile(lambda: pipe.run(dev_imgs)):
+            lst = L.profile(lambda: pipe.run(dev_imgs))
+            if i == prof_steps - 1:
+                order = [(k, round(ms, 4)) for k, ms in lst]
+            for name, ms in lst:
                 per_kernel.setdefault(name, []).append(ms)
         step_ms = sum(sum(v) for v in per_kernel.values()) / prof_steps
         agg = sorted(((sum(v) / prof_steps, len(v) // prof_steps, k) for k, v in per_kernel.items()), reverse=True)
         pk = peaks()
-        top_ms, top_n, top_name = agg[0]
-        # dominant kernel family: the direct 3x3 convolutions of the three CNN trunks (18 launches / step)
+        # dominant kernel family: the tcgen05 conv trunks of the three CNNs (15 tc_conv_kernel launches per step)
         n_aff, n_ori, n_hard = B * int(1.5 * K), n_desc, n_desc
-        conv_flop = n_aff * (FLOP_PER_PATCH["affnet"] - 2 * 3 * 4096) + n_ori * (FLOP_PER_PATCH["orinet"] - 2 * 2 * 9 * 4096) + n_hard * (FLOP_PER_PATCH["hardnet"] - HARD_LAYER_FLOP[6])
-        conv_ms = sum(t for t, n, k in agg if k == "conv3x3_kernel")
-        ach = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        roof = {"kernel": "conv3x3_kernel (18 launches/step: AffNet, OriNet, HardNet trunks)", "bound": "tensor", "achieved": ach,
-                "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"], "traffic": None,
-                "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)", "kernel_ms_per_step": conv_ms,
-                "share_of_step": conv_ms / step_ms if step_ms else None,
+        L1F = {"aff": 2 * 16 * 9 * 1024, "hard": 2 * 32 * 9 * 1024}
+        tc_flop = (n_aff * (FLOP_PER_PATCH["affnet"] - 2 * 3 * 4096 - L1F["aff"]) + n_ori * (FLOP_PER_PATCH["orinet"] - 2 * 2 * 9 * 4096 - L1F["aff"])
+                   + n_hard * (FLOP_PER_PATCH["hardnet"] - HARD_LAYER_FLOP[6] - L1F["hard"]))
+        tc_ms = sum(t for t, n, k in agg if k == "tc_conv_kernel")
+        ach = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+        # bytes the trunks move by construction: every layer reads its input block and writes its output block once
+        roof = {"kernel": "tc_conv_kernel (15 launches/step: conv layers 2-6 of AffNet, OriNet, HardNet; tcgen05 fp16, fp32 accumulate)",
+                "bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"],
+                "traffic": None, "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)", "kernel_ms_per_step": tc_ms,
+                "algorithmic_flop_per_step": tc_flop, "share_of_step": tc_ms / step_ms if step_ms else None,
                 "timing": "CUDA events after every launch over %d profiled steps right after the timed region" % prof_steps,
-                "stages_ms": {k: round(t, 4) for t, n, k in agg}}
-        # HBM roofline of the stencil side (pyramid + detect kernels), reported alongside
+                "stages_ms": {k: round(t, 4) for t, n, k in agg}, "launches_ms": order}
+        cnn_ms = sum(t for t, n, k in agg if k in ("tc_conv_kernel", "first_layer_kernel", "hardnet_head_kernel", "affnet_head_kernel", "orinet_head_kernel", "conv3x3_kernel"))
+        cnn_flop = n_aff * FLOP_PER_PATCH["affnet"] + n_ori * FLOP_PER_PATCH["orinet"] + n_hard * FLOP_PER_PATCH["hardnet"]
+        roof["cnn_all"] = {"kernels": "all CNN kernels (first layer, tc trunks, heads)", "ms_per_step": cnn_ms, "achieved": cnn_flop / (cnn_ms * 1e-3) / 1e12 if cnn_ms else None,
+                           "unit": "TFLOP/s", "algorithmic_flop_per_step": cnn_flop}
+        # HBM roofline of the stencil side (pyramid + detect kernels) and of the sampler, reported alongside
         st_ms = sum(t for t, n, k in agg if k in ("blur_kernel", "detect_level_kernel"))
         roof["stencil"] = {"kernels": "blur_kernel x25 + detect_level_kernel x3", "bound": "hbm", "achieved": ALG_BYTES_PER_PX * B * H * W / (st_ms * 1e-3) / 1e9 if st_ms else None,
                            "peak": pk["hbm"], "unit": "GB/s", "ms_per_step": st_ms}
         if roof["stencil"]["achieved"]:
             roof["stencil"]["frac"] = roof["stencil"]["achieved"] / pk["hbm"]
+        sm_ms = sum(t for t, n, k in agg if k == "extract_patches_pyr_kernel")
+        if sm_ms:
+            sb = (n_aff + n_ori + n_hard) * 8192.0   # 8 KiB per patch per materialised pass
+            roof["sampler"] = {"kernels": "extract_patches_pyr_kernel x3", "bound": "hbm", "achieved": sb / (sm_ms * 1e-3) / 1e9, "peak": pk["hbm"],
+                               "unit": "GB/s", "ms_per_step": sm_ms, "frac": sb / (sm_ms * 1e-3) / 1e9 / pk["hbm"]}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
