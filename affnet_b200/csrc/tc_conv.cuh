@@ -73,6 +73,23 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
                  "l"(bdesc), "r"(idesc), "r"(accumulate)
                  : "memory");
 }
+// Descriptor-lo form: the hi word of every no-swizzle descriptor here is the constant 0x4008 (SBO = 128 B, version 1), so the
+// issuer only does one integer add per operand.  ACC is a compile-time accumulate flag.
+constexpr uint32_t DESC_HI = 0x4008u;
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
+template <int ACC>
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b64 da, db;\n setp.ne.u32 p, %4, 0;\n mov.b64 da, {%1, %5};\n mov.b64 db, {%2, %5};\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}\n" ::"r"(tmem_d),
+        "r"(alo), "r"(blo), "r"(idesc), "n"(ACC), "r"(DESC_HI)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -124,7 +141,7 @@ struct ConvCfg {
     static constexpr int HOUT = H / STRIDE;
     static constexpr int KC = CIN / 8;                  // 16-byte channel groups
     static constexpr int NT = COUT / NSPLIT;            // MMA N
-    static constexpr int NACC = 2;                      // TMEM accumulator buffers
+    static constexpr int NACC = (512 / NT) < 8 ? (512 / NT) : 8;   // TMEM accumulator buffers: the issuer runs up to NACC tiles ahead
     static constexpr int TMEM_COLS = (NACC * NT <= 32) ? 32 : (NACC * NT <= 64) ? 64 : (NACC * NT <= 128) ? 128 : (NACC * NT <= 256) ? 256 : 512;
     static constexpr uint32_t IN_BYTES = (uint32_t)KC * (1 + SA) * In::NPIX * 16;     // one patch
     static constexpr uint32_t W_HALF = 9u * KC * NT * 16;
@@ -137,7 +154,8 @@ struct ConvCfg {
     static constexpr size_t OUT_BYTES = (OUT == FINAL) ? (size_t)COUT * HOUT * HOUT * 4
                                         : (OUT == HEADL) ? (size_t)COUT * HOUT * HOUT * 2
                                                          : (size_t)(COUT / 8) * (1 + OSA) * OUT_NPIX * 16;
-    static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT <= 256, "UMMA shape");
+    static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT <= 128, "UMMA shape / bias staging");
+    static_assert(2 * STAGES + 2 * NACC + 1 <= 60, "barrier area");
     static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -153,12 +171,14 @@ __global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
     uint64_t* tempty = tfull + NACC;                       // [NACC]
     uint64_t* wbar = tempty + NACC;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    float* s_bias = reinterpret_cast<float*>(smem + 512);  // [NT] (NT <= 128)
     unsigned char* sW = smem + 1024;
     unsigned char* sIn = sW + Cfg::W_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.y;
 
+    if (threadIdx.x < NT) s_bias[threadIdx.x] = a.bias[split * NT + threadIdx.x];
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int i = 0; i < NACC; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
@@ -193,48 +213,46 @@ __global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            mbar_wait(wbar, 0);
+        // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues =====
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t leader = elect_one();
+        mbar_wait(wbar, 0);
+        tc_fence_after();
+        const uint32_t w_lo = desc_lo(smem_u32(sW), NT * 16u);
+        int it = 0, tcnt = 0;
+        for (int pi = blockIdx.x; pi < a.n; pi += gridDim.x) {
+            if (!valid(pi)) continue;
+            const int s = it % STAGES;
+            mbar_wait(&full[s], (it / STAGES) & 1);
             tc_fence_after();
-            const uint32_t w_base = smem_u32(sW);
-            int it = 0, tcnt = 0;
-            for (int pi = blockIdx.x; pi < a.n; pi += gridDim.x) {
-                if (!valid(pi)) continue;
-                const int s = it % STAGES;
-                mbar_wait(&full[s], (it / STAGES) & 1);
-                tc_fence_after();
-                const uint32_t in_base = smem_u32(sIn + (size_t)s * Cfg::IN_BYTES);
+            const uint32_t in_lo = desc_lo(smem_u32(sIn + (size_t)s * Cfg::IN_BYTES), In::NPIX * 16u);
 #pragma unroll 1
-                for (int t = 0; t < TILES; t++, tcnt++) {
-                    const int ab = tcnt % NACC;
-                    mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1);
-                    tc_fence_after();
+            for (int t = 0; t < TILES; t++, tcnt++) {
+                const int ab = tcnt % NACC;
+                mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1);
+                tc_fence_after();
+                if (leader) {
                     const uint32_t d_tmem = tmem + (uint32_t)(ab * NT);
+                    const uint32_t a_t = in_lo + (uint32_t)(t * 128);  // 16-byte units
 #pragma unroll
                     for (int tap = 0; tap < 9; tap++) {
-                        const uint32_t a_tap = in_base + (uint32_t)(t * 128 + In::tap_off(tap / 3, tap % 3)) * 16u;
 #pragma unroll
                         for (int j = 0; j < KC / 2; j++) {
-                            const uint64_t da = make_desc(a_tap + (uint32_t)(2 * j) * In::NPIX * 16u, In::NPIX * 16u, 128u);
-                            const uint64_t db = make_desc(w_base + (uint32_t)((tap * KC + 2 * j) * NT) * 16u, NT * 16u, 128u);
-                            umma_f16(d_tmem, da, db, idesc, (tap | j) != 0);
-                            if (SA) {  // A_lo * W_hi
-                                const uint64_t dal = make_desc(a_tap + (uint32_t)(KC + 2 * j) * In::NPIX * 16u, In::NPIX * 16u, 128u);
-                                umma_f16(d_tmem, dal, db, idesc, 1u);
-                            }
-                            if (SW) {  // A_hi * W_lo
-                                const uint64_t dbl = make_desc(w_base + Cfg::W_HALF + (uint32_t)((tap * KC + 2 * j) * NT) * 16u, NT * 16u, 128u);
-                                umma_f16(d_tmem, da, dbl, idesc, 1u);
-                            }
+                            const uint32_t alo = a_t + (uint32_t)(In::tap_off(tap / 3, tap % 3) + 2 * j * In::NPIX);
+                            const uint32_t blo = w_lo + (uint32_t)((tap * KC + 2 * j) * NT);
+                            if (tap == 0 && j == 0) umma_f16_lo<0>(d_tmem, alo, blo, idesc);
+                            else umma_f16_lo<1>(d_tmem, alo, blo, idesc);
+                            if (SA) umma_f16_lo<1>(d_tmem, alo + (uint32_t)(KC * In::NPIX), blo, idesc);          // A_lo * W_hi
+                            if (SW) umma_f16_lo<1>(d_tmem, alo, blo + (uint32_t)(Cfg::W_HALF / 16), idesc);       // A_hi * W_lo
                         }
                     }
                     umma_commit(&tfull[ab]);
                 }
-                umma_commit(&empty[s]);  // all MMAs reading this stage have completed when this arrives
-                it++;
+                __syncwarp();
             }
+            if (leader) umma_commit(&empty[s]);  // all MMAs reading this stage have completed when this arrives
+            __syncwarp();
+            it++;
         }
     } else {
         // ===== epilogue (warps 2..5 -> TMEM lane quadrant warp%4) =====
@@ -293,8 +311,11 @@ __global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
                         for (int g = 0; g < NC / 8; g++) {
                             const int ch = split * NT + c0 + g * 8;
                             float v[8];
-#pragma unroll
-                            for (int e = 0; e < 8; e++) v[e] = fmaxf(__uint_as_float(r[g * 8 + e]) + __ldg(a.bias + ch + e), 0.f);
+                            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8 + 4);
+                            v[0] = fmaxf(__uint_as_float(r[g * 8 + 0]) + b0.x, 0.f); v[1] = fmaxf(__uint_as_float(r[g * 8 + 1]) + b0.y, 0.f);
+                            v[2] = fmaxf(__uint_as_float(r[g * 8 + 2]) + b0.z, 0.f); v[3] = fmaxf(__uint_as_float(r[g * 8 + 3]) + b0.w, 0.f);
+                            v[4] = fmaxf(__uint_as_float(r[g * 8 + 4]) + b1.x, 0.f); v[5] = fmaxf(__uint_as_float(r[g * 8 + 5]) + b1.y, 0.f);
+                            v[6] = fmaxf(__uint_as_float(r[g * 8 + 6]) + b1.z, 0.f); v[7] = fmaxf(__uint_as_float(r[g * 8 + 7]) + b1.w, 0.f);
                             if (OUT == FINAL) {
                                 float* o = reinterpret_cast<float*>(outp);
 #pragma unroll
