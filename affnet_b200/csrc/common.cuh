@@ -54,4 +54,31 @@ __host__ __device__ inline uint32_t float_to_ordered(float f) {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// Bilinear tap with zeros outside the image (F.grid_sample, padding_mode='zeros').  Explicit rounding steps so that the
+// standalone sampler and the sampler fused into the first CNN layer produce identical bits.
+__device__ __forceinline__ float bilinear_zero(const float* __restrict__ img, int h, int w, float px, float py) {
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    const float ax = __fsub_rn(px, fx0), ay = __fsub_rn(py, fy0);
+    const float bx = __fsub_rn(1.f, ax), by = __fsub_rn(1.f, ay);
+    const bool xin0 = (x0 >= 0) & (x0 < w), xin1 = (x0 + 1 >= 0) & (x0 + 1 < w);
+    const bool yin0 = (y0 >= 0) & (y0 < h), yin1 = (y0 + 1 >= 0) & (y0 + 1 < h);
+    const float v00 = (xin0 & yin0) ? __ldg(img + (size_t)y0 * w + x0) : 0.f;
+    const float v01 = (xin1 & yin0) ? __ldg(img + (size_t)y0 * w + x0 + 1) : 0.f;
+    const float v10 = (xin0 & yin1) ? __ldg(img + (size_t)(y0 + 1) * w + x0) : 0.f;
+    const float v11 = (xin1 & yin1) ? __ldg(img + (size_t)(y0 + 1) * w + x0 + 1) : 0.f;
+    const float top = __fmaf_rn(v01, ax, __fmul_rn(v00, bx)), bot = __fmaf_rn(v11, ax, __fmul_rn(v10, bx));
+    return __fmaf_rn(bot, ay, __fmul_rn(top, by));
+}
+
+// Patch-grid coordinate of sample (i,j) of a PSxPS patch under a normalised LAF on an h x w image (LAF.py:313-324).
+__device__ __forceinline__ void laf_sample_xy(const float* __restrict__ L, int h, int w, int i, int j, float inv_ps, float& px, float& py) {
+    const float ms = (float)min(h, w);
+    const float a11 = __fmul_rn(L[0], ms), a12 = __fmul_rn(L[1], ms), tx = __fmul_rn(L[2], (float)w);
+    const float a21 = __fmul_rn(L[3], ms), a22 = __fmul_rn(L[4], ms), ty = __fmul_rn(L[5], (float)h);
+    const float xj = __fsub_rn(__fmul_rn(__fmaf_rn(2.f, (float)j, 1.f), inv_ps), 1.f), yi = __fsub_rn(__fmul_rn(__fmaf_rn(2.f, (float)i, 1.f), inv_ps), 1.f);
+    px = __fsub_rn(__fmaf_rn(a11, xj, __fmaf_rn(a12, yi, tx)), 0.5f);
+    py = __fsub_rn(__fmaf_rn(a21, xj, __fmaf_rn(a22, yi, ty)), 0.5f);
+}
+
 }  // namespace ag

@@ -22,14 +22,18 @@ struct ag_net {
     __half* d_all_h;   // fp16 allocation
 };
 
+#include "tc_conv.cuh"
+
 namespace ag {
 size_t tc_act_bytes(int kind);
 int tc_nsplit(int kind, int layer);
 int tc_split_w(int kind);
-int tc_hardnet_forward(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, void* headbuf,
+tc::FirstSrc tc_src_patches(const float* patches);
+tc::FirstSrc tc_src_pyramid(const ag_pyramid_plan_t* p, const float* pyr, const float* lafs, const int* oct, const int* lvl, int cap);
+int tc_hardnet_forward(const ag_net* net, const tc::FirstSrc& src, int n, int group, const int* count, void* bufA, void* bufB, void* headbuf,
                        float* out, cudaStream_t st);
-int tc_trunk_orinet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
+int tc_trunk_orinet(const ag_net* net, const tc::FirstSrc& src, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
                     cudaStream_t st);
-int tc_trunk_affnet(const ag_net* net, const float* patches, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
+int tc_trunk_affnet(const ag_net* net, const tc::FirstSrc& src, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
                     cudaStream_t st);
 }  // namespace ag

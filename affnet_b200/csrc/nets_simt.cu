@@ -455,9 +455,10 @@ static int trunk_hardnet(const ag_net* net, const float* patches, int n, int gro
 }
 
 // Runs the six conv layers with the net's engine; *feat receives the fp32 NCHW feature pointer ([n,C,8,8]).
-static int run_trunk(const ag_net* net, const float* patches, int n, int group, const int* count, float* a, float* b, float** feat,
-                     cudaStream_t st) {
+static int run_trunk(const ag_net* net, const float* patches, const tc::FirstSrc* pyr_src, int n, int group, const int* count, float* a,
+                     float* b, float** feat, cudaStream_t st) {
     if (net->engine == AG_ENGINE_TC) {
+        const tc::FirstSrc src = pyr_src ? *pyr_src : tc_src_patches(patches);
         // the workspace [a, a + 2*(b-a)) is re-carved as [bufA | bufB | fp32 features]
         char* base = (char*)a;
         const size_t total = 2 * (size_t)((char*)b - (char*)a);
@@ -469,10 +470,11 @@ static int run_trunk(const ag_net* net, const float* patches, int n, int group, 
         b = (float*)(base + 2 * act);
         *feat = b;
         if (net->kind == AG_NET_HARDNET) { set_error("HardNet tensor-core path has its own entry"); return AG_ERR_INVALID; }
-        if (net->kind == AG_NET_ORINET) return tc_trunk_orinet(net, patches, n, group, count, bufA, bufB, b, st);
-        return tc_trunk_affnet(net, patches, n, group, count, bufA, bufB, b, st);
+        if (net->kind == AG_NET_ORINET) return tc_trunk_orinet(net, src, n, group, count, bufA, bufB, b, st);
+        return tc_trunk_affnet(net, src, n, group, count, bufA, bufB, b, st);
     }
     *feat = b;
+    if (patches == nullptr) { set_error("the fp32 SIMT engine needs materialised patches"); return AG_ERR_INVALID; }
     return net->kind == AG_NET_HARDNET ? trunk_hardnet(net, patches, n, group, count, a, b, st)
                                        : trunk_affnet(net, patches, n, group, count, a, b, st);
 }
@@ -492,9 +494,9 @@ static int split_ws(int kind, int n, void* d_ws, size_t ws_bytes, float** a, flo
 
 extern "C" {
 
-int ag_affnet_forward(const ag_net_t* net, const float* d_patches, int n, const int* d_count, int group, float* d_out,
-                      void* d_ws, size_t ws_bytes, void* stream) {
-    AG_REQUIRE(net && d_patches && d_out, "NULL argument");
+static int affnet_impl(const ag_net_t* net, const float* d_patches, const tc::FirstSrc* src, int n, const int* d_count, int group,
+                       float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+    AG_REQUIRE(net && (d_patches || src) && d_out, "NULL argument");
     AG_REQUIRE(net->kind == AG_NET_AFFNET, "not an AffNet handle");
     if (n <= 0) return AG_OK;
     if (group <= 0) group = n;
@@ -502,15 +504,15 @@ int ag_affnet_forward(const ag_net_t* net, const float* d_patches, int n, const 
     int rc = split_ws(net->kind, n, d_ws, ws_bytes, &a, &b);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = run_trunk(net, d_patches, n, group, d_count, a, b, &b, st))) return rc;
+    if ((rc = run_trunk(net, d_patches, src, n, group, d_count, a, b, &b, st))) return rc;
     affnet_head_kernel<<<cdiv(n, 8), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, n, group, d_count);
     AG_CHECK_LAUNCH("affnet_head_kernel");
     return AG_OK;
 }
 
-int ag_orinet_forward(const ag_net_t* net, const float* d_patches, int n, const int* d_count, int group, float* d_out,
-                      float* d_angle, void* d_ws, size_t ws_bytes, void* stream) {
-    AG_REQUIRE(net && d_patches && (d_out || d_angle), "NULL argument");
+static int orinet_impl(const ag_net_t* net, const float* d_patches, const tc::FirstSrc* src, int n, const int* d_count, int group,
+                       float* d_out, float* d_angle, void* d_ws, size_t ws_bytes, void* stream) {
+    AG_REQUIRE(net && (d_patches || src) && (d_out || d_angle), "NULL argument");
     AG_REQUIRE(net->kind == AG_NET_ORINET, "not an OriNet handle");
     if (n <= 0) return AG_OK;
     if (group <= 0) group = n;
@@ -518,15 +520,15 @@ int ag_orinet_forward(const ag_net_t* net, const float* d_patches, int n, const 
     int rc = split_ws(net->kind, n, d_ws, ws_bytes, &a, &b);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = run_trunk(net, d_patches, n, group, d_count, a, b, &b, st))) return rc;
+    if ((rc = run_trunk(net, d_patches, src, n, group, d_count, a, b, &b, st))) return rc;
     orinet_head_kernel<<<cdiv(n, 8), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, d_angle, n, group, d_count);
     AG_CHECK_LAUNCH("orinet_head_kernel");
     return AG_OK;
 }
 
-int ag_hardnet_forward(const ag_net_t* net, const float* d_patches, int n, const int* d_count, int group, float* d_out,
-                       void* d_ws, size_t ws_bytes, void* stream) {
-    AG_REQUIRE(net && d_patches && d_out, "NULL argument");
+static int hardnet_impl(const ag_net_t* net, const float* d_patches, const tc::FirstSrc* src, int n, const int* d_count, int group,
+                        float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+    AG_REQUIRE(net && (d_patches || src) && d_out, "NULL argument");
     AG_REQUIRE(net->kind == AG_NET_HARDNET, "not a HardNet handle");
     if (n <= 0) return AG_OK;
     if (group <= 0) group = n;
@@ -537,12 +539,42 @@ int ag_hardnet_forward(const ag_net_t* net, const float* d_patches, int n, const
     if (net->engine == AG_ENGINE_TC) {
         char* base = (char*)d_ws;
         const size_t act = align_up((size_t)n * tc_act_bytes(net->kind), 256);
-        return tc_hardnet_forward(net, d_patches, n, group, d_count, base, base + act, base + 2 * act, d_out, st);
+        const tc::FirstSrc s0 = src ? *src : tc_src_patches(d_patches);
+        return tc_hardnet_forward(net, s0, n, group, d_count, base, base + act, base + 2 * act, d_out, st);
     }
-    if ((rc = run_trunk(net, d_patches, n, group, d_count, a, b, &b, st))) return rc;
+    if ((rc = run_trunk(net, d_patches, src, n, group, d_count, a, b, &b, st))) return rc;
     hardnet_head_kernel<<<cdiv(n, HH_P), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, n, group, d_count);
     AG_CHECK_LAUNCH("hardnet_head_kernel");
     return AG_OK;
+}
+
+int ag_affnet_forward(const ag_net_t* net, const float* d_patches, int n, const int* d_count, int group, float* d_out, void* d_ws,
+                      size_t ws_bytes, void* stream) {
+    AG_REQUIRE(d_patches, "NULL patches");
+    return affnet_impl(net, d_patches, nullptr, n, d_count, group, d_out, d_ws, ws_bytes, stream);
+}
+int ag_orinet_forward(const ag_net_t* net, const float* d_patches, int n, const int* d_count, int group, float* d_out, float* d_angle,
+                      void* d_ws, size_t ws_bytes, void* stream) {
+    AG_REQUIRE(d_patches, "NULL patches");
+    return orinet_impl(net, d_patches, nullptr, n, d_count, group, d_out, d_angle, d_ws, ws_bytes, stream);
+}
+int ag_hardnet_forward(const ag_net_t* net, const float* d_patches, int n, const int* d_count, int group, float* d_out, void* d_ws,
+                       size_t ws_bytes, void* stream) {
+    AG_REQUIRE(d_patches, "NULL patches");
+    return hardnet_impl(net, d_patches, nullptr, n, d_count, group, d_out, d_ws, ws_bytes, stream);
+}
+
+// Fused sampler + net: patches are sampled from the pyramid inside the first tensor-core layer (tensor-core engine only).
+int ag_net_forward_pyr(const ag_net_t* net, const ag_pyramid_plan_t* plan, const float* d_pyr, const float* d_lafs, const int* d_oct,
+                       const int* d_lvl, const int* d_count, int cap, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+    AG_REQUIRE(net && plan && d_pyr && d_lafs && d_oct && d_lvl && d_out, "NULL argument");
+    AG_REQUIRE(cap >= 1, "bad capacity");
+    AG_REQUIRE(net->engine == AG_ENGINE_TC, "fused sampling needs the tensor-core engine");
+    const tc::FirstSrc src = tc_src_pyramid(plan, d_pyr, d_lafs, d_oct, d_lvl, cap);
+    const int n = plan->B * cap;
+    if (net->kind == AG_NET_AFFNET) return affnet_impl(net, nullptr, &src, n, d_count, cap, d_out, d_ws, ws_bytes, stream);
+    if (net->kind == AG_NET_ORINET) return orinet_impl(net, nullptr, &src, n, d_count, cap, d_out, nullptr, d_ws, ws_bytes, stream);
+    return hardnet_impl(net, nullptr, &src, n, d_count, cap, d_out, d_ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -45,7 +45,7 @@ int ag_pipeline_create(const ag_pipeline_config_t* cfg, const ag_net_t* affnet, 
     p->off_oct1 = take(sizeof(int) * B * M);
     p->off_lvl1 = take(sizeof(int) * B * M);
     p->off_cnt1 = take(sizeof(int) * B);
-    p->off_patches = take(sizeof(float) * B * M * 1024);
+    p->off_patches = 0;  // 32x32 patches are never materialised: the sampler is fused into the first tensor-core layer
     p->off_A = take(sizeof(float) * B * M * 4);
     p->off_lafs2 = take(sizeof(float) * B * K * 6);
     p->off_oct2 = take(sizeof(int) * B * K);
@@ -81,7 +81,7 @@ int ag_pipeline_run(ag_pipeline_t* p, const float* d_img, void* d_ws, size_t ws_
     float* pyr = (float*)(ws + p->off_pyr);
     float* resp1 = (float*)(ws + p->off_resp1); float* lafs1 = (float*)(ws + p->off_lafs1);
     int* oct1 = (int*)(ws + p->off_oct1); int* lvl1 = (int*)(ws + p->off_lvl1); int* cnt1 = (int*)(ws + p->off_cnt1);
-    float* patches = (float*)(ws + p->off_patches); float* A = (float*)(ws + p->off_A);
+    float* A = (float*)(ws + p->off_A);
     float* lafs2 = (float*)(ws + p->off_lafs2); int* oct2 = (int*)(ws + p->off_oct2); int* lvl2 = (int*)(ws + p->off_lvl2);
     float* nlafs = (float*)(ws + p->off_nlafs); int* oct3 = (int*)(ws + p->off_oct3); int* lvl3 = (int*)(ws + p->off_lvl3);
     void* netws = ws + p->off_net;
@@ -93,12 +93,10 @@ int ag_pipeline_run(ag_pipeline_t* p, const float* d_img, void* d_ws, size_t ws_
     if ((rc = ag_detect(&p->plan, pyr, 0.f, (int)c.mrSize, &det, stream))) return rc;
     if ((rc = ag_select_keypoints(&p->plan, &det, M, (float)c.mrSize, M, resp1, lafs1, oct1, lvl1, cnt1, stream))) return rc;
     // affine shape (one AffNet iteration)
-    if ((rc = ag_extract_patches_pyr(&p->plan, pyr, lafs1, oct1, lvl1, cnt1, M, 32, patches, stream))) return rc;
-    if ((rc = ag_affnet_forward(p->aff, patches, B * M, cnt1, M, A, netws, p->net_bytes, stream))) return rc;
+    if ((rc = ag_net_forward_pyr(p->aff, &p->plan, pyr, lafs1, oct1, lvl1, cnt1, M, A, netws, p->net_bytes, stream))) return rc;
     if ((rc = ag_affine_shape_filter(A, resp1, lafs1, oct1, lvl1, cnt1, B, M, K, K, d_resp, lafs2, oct2, lvl2, d_count, stream))) return rc;
     if (c.do_ori) {
-        if ((rc = ag_extract_patches_pyr(&p->plan, pyr, lafs2, oct2, lvl2, d_count, K, 32, patches, stream))) return rc;
-        if ((rc = ag_orinet_forward(p->ori, patches, B * K, d_count, K, A, nullptr, netws, p->net_bytes, stream))) return rc;
+        if ((rc = ag_net_forward_pyr(p->ori, &p->plan, pyr, lafs2, oct2, lvl2, d_count, K, A, netws, p->net_bytes, stream))) return rc;
         if ((rc = ag_lafs_apply_rotation(lafs2, A, B * K, stream))) return rc;
     }
     // denormalizeLAFs (LAF.py:407-417), then descriptor patches: level choice + normalizeLAFs (LAF.py:419-429)
@@ -106,8 +104,7 @@ int ag_pipeline_run(ag_pipeline_t* p, const float* d_img, void* d_ws, size_t ws_
     if ((rc = ag_lafs_scale(lafs2, d_lafs, B * K, ms, (float)c.W, (float)c.H, stream))) return rc;
     if ((rc = ag_pyramid_level_for_lafs(&p->plan, d_lafs, B * K, 32, oct3, lvl3, stream))) return rc;
     if ((rc = ag_lafs_scale(d_lafs, nlafs, B * K, 1.0f / ms, (float)(1.0 / (double)c.W), (float)(1.0 / (double)c.H), stream))) return rc;
-    if ((rc = ag_extract_patches_pyr(&p->plan, pyr, nlafs, oct3, lvl3, d_count, K, 32, patches, stream))) return rc;
-    if ((rc = ag_hardnet_forward(p->hard, patches, B * K, d_count, K, d_desc, netws, p->net_bytes, stream))) return rc;
+    if ((rc = ag_net_forward_pyr(p->hard, &p->plan, pyr, nlafs, oct3, lvl3, d_count, K, d_desc, netws, p->net_bytes, stream))) return rc;
     p->launches = g_launches - launches0;
     return AG_OK;
 }

@@ -13,41 +13,14 @@
 
 namespace ag {
 
-__device__ __forceinline__ float bilinear_zero(const float* __restrict__ img, int h, int w, float px, float py) {
-    const float fx0 = floorf(px), fy0 = floorf(py);
-    const int x0 = (int)fx0, y0 = (int)fy0;
-    const float ax = px - fx0, ay = py - fy0;
-    const bool xin0 = (x0 >= 0) & (x0 < w), xin1 = (x0 + 1 >= 0) & (x0 + 1 < w);
-    const bool yin0 = (y0 >= 0) & (y0 < h), yin1 = (y0 + 1 >= 0) & (y0 + 1 < h);
-    const float v00 = (xin0 & yin0) ? __ldg(img + (size_t)y0 * w + x0) : 0.f;
-    const float v01 = (xin1 & yin0) ? __ldg(img + (size_t)y0 * w + x0 + 1) : 0.f;
-    const float v10 = (xin0 & yin1) ? __ldg(img + (size_t)(y0 + 1) * w + x0) : 0.f;
-    const float v11 = (xin1 & yin1) ? __ldg(img + (size_t)(y0 + 1) * w + x0 + 1) : 0.f;
-    return v00 * (1.f - ax) * (1.f - ay) + v01 * ax * (1.f - ay) + v10 * (1.f - ax) * ay + v11 * ax * ay;
-}
-
-struct LafPx {
-    float a11, a12, a21, a22, tx, ty;
-};
-
-__device__ __forceinline__ LafPx laf_to_px(const float* __restrict__ L, int h, int w) {
-    const float ms = (float)min(h, w);
-    LafPx r;
-    r.a11 = L[0] * ms; r.a12 = L[1] * ms; r.tx = L[2] * (float)w;
-    r.a21 = L[3] * ms; r.a22 = L[4] * ms; r.ty = L[5] * (float)h;
-    return r;
-}
-
 __global__ void extract_patches_kernel(const float* __restrict__ img, int C, int h, int w, int per_patch_img,
                                        const float* __restrict__ lafs, int n, int PS, float* __restrict__ out) {
     const int pi = blockIdx.y;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= PS * PS) return;
     const int i = t / PS, j = t - i * PS;
-    const LafPx A = laf_to_px(lafs + (size_t)pi * 6, h, w);
-    const float xj = (2.f * j + 1.f) / (float)PS - 1.f, yi = (2.f * i + 1.f) / (float)PS - 1.f;
-    const float px = fmaf(A.a11, xj, fmaf(A.a12, yi, A.tx)) - 0.5f;
-    const float py = fmaf(A.a21, xj, fmaf(A.a22, yi, A.ty)) - 0.5f;
+    float px, py;
+    laf_sample_xy(lafs + (size_t)pi * 6, h, w, i, j, 1.0f / (float)PS, px, py);
     const float* base = img + (per_patch_img ? (size_t)pi * C * h * w : 0);
     for (int c = 0; c < C; c++)
         out[((size_t)pi * C + c) * PS * PS + t] = bilinear_zero(base + (size_t)c * h * w, h, w, px, py);
@@ -81,10 +54,8 @@ __global__ void extract_patches_pyr_kernel(const PyrGeom G, const float* __restr
     const int h = G.h[o], w = G.w[o];
     const float* img = pyr + G.off[o][l] + (size_t)b * h * w;
     const int i = t / PS, j = t - i * PS;
-    const LafPx A = laf_to_px(lafs + row * 6, h, w);
-    const float xj = (2.f * j + 1.f) / (float)PS - 1.f, yi = (2.f * i + 1.f) / (float)PS - 1.f;
-    const float px = fmaf(A.a11, xj, fmaf(A.a12, yi, A.tx)) - 0.5f;
-    const float py = fmaf(A.a21, xj, fmaf(A.a22, yi, A.ty)) - 0.5f;
+    float px, py;
+    laf_sample_xy(lafs + row * 6, h, w, i, j, 1.0f / (float)PS, px, py);
     out[row * PS * PS + t] = bilinear_zero(img, h, w, px, py);
 }
 

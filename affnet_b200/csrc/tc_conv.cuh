@@ -121,6 +121,25 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Source of the fused first layer (FIRST = 1): either materialised patches [n,32,32] fp32, or the pyramid + keypoints
+// (the affine bilinear sampler of LAF.py:313-372 runs inside the kernel; patches never touch HBM).
+struct PyrGeomTC {
+    int n_octaves, n_levels;
+    int h[AG_MAX_OCTAVES], w[AG_MAX_OCTAVES];
+    long long off[AG_MAX_OCTAVES][AG_MAX_LEVELS];
+};
+struct FirstSrc {
+    const float* patches;   // if non-NULL: [n][32][32]
+    const float* pyr;       // else: pyramid base, rows (b, i) = (pi / cap, pi % cap)
+    const float* lafs;      // [B*cap][2][3] normalised
+    const int* oct;
+    const int* lvl;
+    int cap;
+    const float* w1;        // [9][C1] fp32 (BatchNorm folded)
+    const float* b1;        // [C1]
+    PyrGeomTC geom;
+};
+
 struct ConvArgs {
     const __half* in;     // [n][CIN/8][NPIX_IN][8]
     void* out;            // next layer's canonical fp16 buffer, or fp32 [n][COUT][HOUT][HOUT]
@@ -135,7 +154,7 @@ struct ConvArgs {
 // Split precision (fp32-grade results from fp16 tensor cores): SA = the input carries hi and lo fp16 planes
 // (x = hi + lo, channel groups [0,KC) hi then [KC,2KC) lo), SW = the weights carry hi and lo copies, OSA = write the
 // output as hi/lo planes.  D = A_hi W_hi (+ A_lo W_hi if SA) (+ A_hi W_lo if SW); the lo*lo term (2^-22) is dropped.
-template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA = 0, int SW = 0, int OSA = 0>
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA = 0, int SW = 0, int OSA = 0, int FIRST = 0>
 struct ConvCfg {
     using In = InLay<H, STRIDE>;
     static constexpr int HOUT = H / STRIDE;
@@ -146,7 +165,9 @@ struct ConvCfg {
     static constexpr uint32_t IN_BYTES = (uint32_t)KC * (1 + SA) * In::NPIX * 16;     // one patch
     static constexpr uint32_t W_HALF = 9u * KC * NT * 16;
     static constexpr uint32_t W_BYTES = W_HALF * (1 + SW);
-    static constexpr size_t SMEM = 1024 + (size_t)W_BYTES + (size_t)STAGES * IN_BYTES;
+    static constexpr int THREADS = FIRST ? 448 : 192;   // FIRST adds 8 producer warps (sampler + input_norm + conv1)
+    static constexpr size_t FIRST_BYTES = FIRST ? (size_t)(2 * 34 * 36 + 9 * CIN + CIN + 64) * 4 : 0;
+    static constexpr size_t SMEM = 1024 + (size_t)W_BYTES + (size_t)STAGES * IN_BYTES + FIRST_BYTES;
     // output buffer geometry
     using OutP = InLay<HOUT, 1>;   // if the consumer has stride 1
     using OutS = InLay<HOUT, 2>;   // if the consumer has stride 2
@@ -159,9 +180,9 @@ struct ConvCfg {
     static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA>
-__global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
-    using Cfg = ConvCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA>;
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int FIRST>
+__global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const ConvArgs a, const FirstSrc src) {
+    using Cfg = ConvCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, FIRST>;
     using In = typename Cfg::In;
     constexpr int KC = Cfg::KC, NT = Cfg::NT, NACC = Cfg::NACC, TILES = In::TILES, HOUT = Cfg::HOUT;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -180,7 +201,7 @@ __global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
 
     if (threadIdx.x < NT) s_bias[threadIdx.x] = a.bias[split * NT + threadIdx.x];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], FIRST ? 256 : 1); mbar_init(&empty[s], 1); }
         for (int i = 0; i < NACC; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -202,7 +223,7 @@ __global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
             mbar_expect_tx(wbar, Cfg::W_BYTES);
             bulk_g2s(sW, reinterpret_cast<const unsigned char*>(a.wpk) + (size_t)split * Cfg::W_BYTES, Cfg::W_BYTES, wbar);
             int it = 0;
-            for (int pi = blockIdx.x; pi < a.n; pi += gridDim.x) {
+            for (int pi = blockIdx.x; pi < a.n && !FIRST; pi += gridDim.x) {
                 if (!valid(pi)) continue;
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
@@ -254,7 +275,104 @@ __global__ void __launch_bounds__(192, 1) tc_conv_kernel(const ConvArgs a) {
             __syncwarp();
             it++;
         }
-    } else {
+    } else if (FIRST && warp >= 6) {
+        // ===== fused first layer: sampler (or patch load) -> input_norm -> conv3x3(1 -> CIN) + ReLU -> fp16 stage =====
+        static_assert(!FIRST || (H == 32 && STRIDE == 1), "the first conv layer feeds a stride-1 32x32 layer");
+        float* s_patch = reinterpret_cast<float*>(sIn + (size_t)STAGES * Cfg::IN_BYTES);  // [2][34][36]
+        float* s_w1 = s_patch + 2 * 34 * 36;                                               // [9][CIN]
+        float* s_b1 = s_w1 + 9 * CIN;                                                      // [CIN]
+        float* s_red = s_b1 + CIN;                                                         // [8][2] (+pad)
+        const int pt = threadIdx.x - 192;  // 0..255
+        for (int i = pt; i < 9 * CIN; i += 256) s_w1[i] = src.w1[i];
+        if (pt < CIN) s_b1[pt] = src.b1[pt];
+        for (int i = pt; i < 2 * 34 * 36; i += 256) s_patch[i] = 0.f;
+        // the zero border / slack of the stages is written once: conv1 only ever writes interior slots
+        for (int i = pt; i < (int)(STAGES * Cfg::IN_BYTES / 16); i += 256) reinterpret_cast<uint4*>(sIn)[i] = make_uint4(0, 0, 0, 0);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        int it = 0;
+        for (int pi = blockIdx.x; pi < a.n; pi += gridDim.x) {
+            if (!valid(pi)) continue;
+            const int s = it % STAGES;
+            float* sp = s_patch + (it & 1) * 34 * 36;
+            // 1. fetch 4 pixels per thread
+            float v4[4];
+            if (src.patches != nullptr) {
+                const float* pp = src.patches + (size_t)pi * 1024;
+#pragma unroll
+                for (int k = 0; k < 4; k++) v4[k] = pp[pt + k * 256];
+            } else {
+                const int b = pi / src.cap;
+                const int o = min(max(src.oct[pi], 0), src.geom.n_octaves - 1), l = min(max(src.lvl[pi], 0), src.geom.n_levels - 1);
+                const int h = src.geom.h[o], w = src.geom.w[o];
+                const float* img = src.pyr + src.geom.off[o][l] + (size_t)b * h * w;
+                const float* Lf = src.lafs + (size_t)pi * 6;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int p = pt + k * 256;
+                    float px, py;
+                    laf_sample_xy(Lf, h, w, p >> 5, p & 31, 1.0f / 32.0f, px, py);
+                    v4[k] = bilinear_zero(img, h, w, px, py);
+                }
+            }
+            // 2. input_norm statistics over the 256 producer threads
+            float sm = (v4[0] + v4[1]) + (v4[2] + v4[3]);
+            for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+            if (lane == 0) s_red[(warp - 6) * 2 + (it & 1) * 16] = sm;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            sm = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) sm += s_red[i * 2 + (it & 1) * 16];
+            const float mean = sm / 1024.f;
+            float q = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const float d = v4[k] - mean; q = fmaf(d, d, q); }
+            for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            if (lane == 0) s_red[(warp - 6) * 2 + 1 + (it & 1) * 16] = q;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int p = pt + k * 256; sp[((p >> 5) + 1) * 36 + (p & 31) + 1] = v4[k] - mean; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            q = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) q += s_red[i * 2 + 1 + (it & 1) * 16];
+            const float inv = 1.f / (sqrtf(q / 1023.f) + 1e-7f);
+            // 3. conv1 + ReLU -> fp16 canonical stage (wait until the MMAs of the previous use of this stage are done)
+            mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+            unsigned char* st = sIn + (size_t)s * Cfg::IN_BYTES;
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) {
+                const int p = pt + k * 256, y = p >> 5, x = p & 31;
+                float acc[CIN];
+#pragma unroll
+                for (int c = 0; c < CIN; c++) acc[c] = s_b1[c];
+#pragma unroll
+                for (int tap = 0; tap < 9; tap++) {
+                    const float av = sp[(y + tap / 3) * 36 + x + tap % 3] * inv;
+#pragma unroll
+                    for (int c = 0; c < CIN; c++) acc[c] = fmaf(av, s_w1[tap * CIN + c], acc[c]);
+                }
+                const int slot = In::slot(y + 1, x + 1);
+#pragma unroll
+                for (int g = 0; g < CIN / 8; g++) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[e] = fmaxf(acc[g * 8 + e], 0.f);
+                    uint4 pk;
+                    pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
+                    *reinterpret_cast<uint4*>(st + ((size_t)g * In::NPIX + slot) * 16) = pk;
+                    if (SA) {
+                        float lo[8];
+#pragma unroll
+                        for (int e = 0; e < 8; e++) lo[e] = v[e] - __half2float(__float2half_rn(v[e]));
+                        pk.x = pack_h2(lo[0], lo[1]); pk.y = pack_h2(lo[2], lo[3]); pk.z = pack_h2(lo[4], lo[5]); pk.w = pack_h2(lo[6], lo[7]);
+                        *reinterpret_cast<uint4*>(st + ((size_t)(CIN / 8 + g) * In::NPIX + slot) * 16) = pk;
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(&full[s]);
+            it++;
+        }
+    } else if (warp >= 2 && warp < 6) {
         // ===== epilogue (warps 2..5 -> TMEM lane quadrant warp%4) =====
         const int q = warp & 3;
         const int et = (warp - 2) * 32 + lane;  // 0..127

@@ -180,6 +180,12 @@ int ag_orinet_forward(const ag_net_t* net, const float* d_patches, int n, const 
 int ag_hardnet_forward(const ag_net_t* net, const float* d_patches, int n, const int* d_count, int group, float* d_out,
                        void* d_ws, size_t ws_bytes, void* stream);
 
+/* Fused sampler + net (tensor-core engine): LAF i of image b is sampled at pyr[oct][lvl] INSIDE the first tensor-core
+ * layer (32x32 patches never touch HBM), then the net runs as above.  Layout as ag_extract_patches_pyr: d_lafs
+ * [B,cap,2,3] normalised, d_oct/d_lvl [B,cap], d_count [B] or NULL.  d_out: [B*cap,2,2] (AffNet, OriNet) or [B*cap,128]. */
+int ag_net_forward_pyr(const ag_net_t* net, const ag_pyramid_plan_t* plan, const float* d_pyr, const float* d_lafs, const int* d_oct,
+                       const int* d_lvl, const int* d_count, int cap, float* d_out, void* d_ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Keypoint geometry                 replaces getAffineShape's filter (SparseImgRepresenter.py:136-162,
  *                                   Utils.py:168-175, LAF.py:98-104), getOrientation's compose (:175),
