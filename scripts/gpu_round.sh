@@ -12,7 +12,12 @@ tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --batch 4 --no-cpu-baseline --no-graph > gpurun_out/ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:${NCU_KERNEL:-conv3x3_kernel<32, 32, 32}" -c 2 \
-    -o gpurun_out/prof_top -f python bench.py --steps 1 --warmup 3 --batch 4 --no-cpu-baseline --no-graph > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:${NCU_KERNEL:-tc_conv_kernel}" -s ${NCU_SKIP:-0} -c ${NCU_COUNT:-3} \
+    -o gpurun_out/prof_top -f python bench.py --steps 1 --warmup 3 --batch 2 --no-cpu-baseline --no-graph > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
+fi
+
+if [ "${NCU_DETECT:-0}" = "1" ]; then
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:detect_level_kernel|blur_kernel" -c 8 \
+    -o gpurun_out/prof_stencil -f python bench.py --steps 1 --warmup 3 --batch 16 --no-cpu-baseline --no-graph > gpurun_out/ncu_stencil.log 2>&1
 fi
