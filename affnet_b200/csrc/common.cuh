@@ -71,6 +71,24 @@ __device__ __forceinline__ float bilinear_zero(const float* __restrict__ img, in
     return __fmaf_rn(bot, ay, __fmul_rn(top, by));
 }
 
+// The same tap in two phases (issue the four loads early, combine later); bit-identical to bilinear_zero.
+__device__ __forceinline__ void bilinear_taps(const float* __restrict__ img, int h, int w, float px, float py, float (&t)[4], float& ax, float& ay) {
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    ax = __fsub_rn(px, fx0); ay = __fsub_rn(py, fy0);
+    const bool xin0 = (x0 >= 0) & (x0 < w), xin1 = (x0 + 1 >= 0) & (x0 + 1 < w);
+    const bool yin0 = (y0 >= 0) & (y0 < h), yin1 = (y0 + 1 >= 0) & (y0 + 1 < h);
+    t[0] = (xin0 & yin0) ? __ldg(img + (size_t)y0 * w + x0) : 0.f;
+    t[1] = (xin1 & yin0) ? __ldg(img + (size_t)y0 * w + x0 + 1) : 0.f;
+    t[2] = (xin0 & yin1) ? __ldg(img + (size_t)(y0 + 1) * w + x0) : 0.f;
+    t[3] = (xin1 & yin1) ? __ldg(img + (size_t)(y0 + 1) * w + x0 + 1) : 0.f;
+}
+__device__ __forceinline__ float bilinear_combine(const float (&t)[4], float ax, float ay) {
+    const float bx = __fsub_rn(1.f, ax), by = __fsub_rn(1.f, ay);
+    const float top = __fmaf_rn(t[1], ax, __fmul_rn(t[0], bx)), bot = __fmaf_rn(t[3], ax, __fmul_rn(t[2], bx));
+    return __fmaf_rn(bot, ay, __fmul_rn(top, by));
+}
+
 // Patch-grid coordinate of sample (i,j) of a PSxPS patch under a normalised LAF on an h x w image (LAF.py:313-324).
 __device__ __forceinline__ void laf_sample_xy(const float* __restrict__ L, int h, int w, int i, int j, float inv_ps, float& px, float& py) {
     const float ms = (float)min(h, w);

@@ -289,17 +289,14 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
         // the zero border / slack of the stages is written once: conv1 only ever writes interior slots
         for (int i = pt; i < (int)(STAGES * Cfg::IN_BYTES / 16); i += 256) reinterpret_cast<uint4*>(sIn)[i] = make_uint4(0, 0, 0, 0);
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        int it = 0;
-        for (int pi = blockIdx.x; pi < a.n; pi += gridDim.x) {
-            if (!valid(pi)) continue;
-            const int s = it % STAGES;
-            float* sp = s_patch + (it & 1) * 34 * 36;
-            // 1. fetch 4 pixels per thread
-            float v4[4];
+        // raw bilinear taps of the NEXT patch are requested before the conv of the current one so that their latency hides
+        // behind compute (software prefetch): 16 values + the two fractional weights per pixel.
+        float tp[4][4], fx[4], fy[4];
+        auto issue_fetch = [&](int pi) {
             if (src.patches != nullptr) {
                 const float* pp = src.patches + (size_t)pi * 1024;
 #pragma unroll
-                for (int k = 0; k < 4; k++) v4[k] = pp[pt + k * 256];
+                for (int k = 0; k < 4; k++) { tp[k][0] = pp[pt + k * 256]; tp[k][1] = tp[k][2] = tp[k][3] = 0.f; fx[k] = 0.f; fy[k] = 0.f; }
             } else {
                 const int b = pi / src.cap;
                 const int o = min(max(src.oct[pi], 0), src.geom.n_octaves - 1), l = min(max(src.lvl[pi], 0), src.geom.n_levels - 1);
@@ -311,9 +308,23 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
                     const int p = pt + k * 256;
                     float px, py;
                     laf_sample_xy(Lf, h, w, p >> 5, p & 31, 1.0f / 32.0f, px, py);
-                    v4[k] = bilinear_zero(img, h, w, px, py);
+                    bilinear_taps(img, h, w, px, py, tp[k], fx[k], fy[k]);
                 }
             }
+        };
+        int pi = blockIdx.x;
+        while (pi < a.n && !valid(pi)) pi += gridDim.x;
+        if (pi < a.n) issue_fetch(pi);
+        int it = 0;
+        while (pi < a.n) {
+            const int s = it % STAGES;
+            float* sp = s_patch + (it & 1) * 34 * 36;
+            float v4[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) v4[k] = bilinear_combine(tp[k], fx[k], fy[k]);
+            int pn = pi + gridDim.x;
+            while (pn < a.n && !valid(pn)) pn += gridDim.x;
+            if (pn < a.n) issue_fetch(pn);
             // 2. input_norm statistics over the 256 producer threads
             float sm = (v4[0] + v4[1]) + (v4[2] + v4[3]);
             for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
@@ -339,38 +350,50 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
             mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
             unsigned char* st = sIn + (size_t)s * Cfg::IN_BYTES;
 #pragma unroll 1
-            for (int k = 0; k < 4; k++) {
-                const int p = pt + k * 256, y = p >> 5, x = p & 31;
-                float acc[CIN];
+            for (int k2 = 0; k2 < 2; k2++) {  // two pixels at a time: weights are read once for both
+                const int p0 = pt + (2 * k2) * 256, p1 = p0 + 256;
+                const int y0 = p0 >> 5, x0 = p0 & 31, y1 = p1 >> 5, x1 = p1 & 31;
+                float acc0[CIN], acc1[CIN];
 #pragma unroll
-                for (int c = 0; c < CIN; c++) acc[c] = s_b1[c];
+                for (int c = 0; c < CIN; c++) { acc0[c] = s_b1[c]; acc1[c] = acc0[c]; }
 #pragma unroll
                 for (int tap = 0; tap < 9; tap++) {
-                    const float av = sp[(y + tap / 3) * 36 + x + tap % 3] * inv;
+                    const float av0 = sp[(y0 + tap / 3) * 36 + x0 + tap % 3] * inv, av1 = sp[(y1 + tap / 3) * 36 + x1 + tap % 3] * inv;
 #pragma unroll
-                    for (int c = 0; c < CIN; c++) acc[c] = fmaf(av, s_w1[tap * CIN + c], acc[c]);
+                    for (int c4 = 0; c4 < CIN / 4; c4++) {
+                        const float4 wv = *reinterpret_cast<const float4*>(s_w1 + tap * CIN + c4 * 4);
+                        acc0[c4 * 4 + 0] = fmaf(av0, wv.x, acc0[c4 * 4 + 0]); acc1[c4 * 4 + 0] = fmaf(av1, wv.x, acc1[c4 * 4 + 0]);
+                        acc0[c4 * 4 + 1] = fmaf(av0, wv.y, acc0[c4 * 4 + 1]); acc1[c4 * 4 + 1] = fmaf(av1, wv.y, acc1[c4 * 4 + 1]);
+                        acc0[c4 * 4 + 2] = fmaf(av0, wv.z, acc0[c4 * 4 + 2]); acc1[c4 * 4 + 2] = fmaf(av1, wv.z, acc1[c4 * 4 + 2]);
+                        acc0[c4 * 4 + 3] = fmaf(av0, wv.w, acc0[c4 * 4 + 3]); acc1[c4 * 4 + 3] = fmaf(av1, wv.w, acc1[c4 * 4 + 3]);
+                    }
                 }
-                const int slot = In::slot(y + 1, x + 1);
 #pragma unroll
-                for (int g = 0; g < CIN / 8; g++) {
-                    float v[8];
+                for (int half = 0; half < 2; half++) {
+                    const float* acc = half ? acc1 : acc0;
+                    const int slot = half ? In::slot(y1 + 1, x1 + 1) : In::slot(y0 + 1, x0 + 1);
 #pragma unroll
-                    for (int e = 0; e < 8; e++) v[e] = fmaxf(acc[g * 8 + e], 0.f);
-                    uint4 pk;
-                    pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
-                    *reinterpret_cast<uint4*>(st + ((size_t)g * In::NPIX + slot) * 16) = pk;
-                    if (SA) {
-                        float lo[8];
+                    for (int g = 0; g < CIN / 8; g++) {
+                        float v[8];
 #pragma unroll
-                        for (int e = 0; e < 8; e++) lo[e] = v[e] - __half2float(__float2half_rn(v[e]));
-                        pk.x = pack_h2(lo[0], lo[1]); pk.y = pack_h2(lo[2], lo[3]); pk.z = pack_h2(lo[4], lo[5]); pk.w = pack_h2(lo[6], lo[7]);
-                        *reinterpret_cast<uint4*>(st + ((size_t)(CIN / 8 + g) * In::NPIX + slot) * 16) = pk;
+                        for (int e = 0; e < 8; e++) v[e] = fmaxf(acc[g * 8 + e], 0.f);
+                        uint4 pk;
+                        pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
+                        *reinterpret_cast<uint4*>(st + ((size_t)g * In::NPIX + slot) * 16) = pk;
+                        if (SA) {
+                            float lo[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e++) lo[e] = v[e] - __half2float(__float2half_rn(v[e]));
+                            pk.x = pack_h2(lo[0], lo[1]); pk.y = pack_h2(lo[2], lo[3]); pk.z = pack_h2(lo[4], lo[5]); pk.w = pack_h2(lo[6], lo[7]);
+                            *reinterpret_cast<uint4*>(st + ((size_t)(CIN / 8 + g) * In::NPIX + slot) * 16) = pk;
+                        }
                     }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
             mbar_arrive(&full[s]);
             it++;
+            pi = pn;
         }
     } else if (warp >= 2 && warp < 6) {
         // ===== epilogue (warps 2..5 -> TMEM lane quadrant warp%4) =====
