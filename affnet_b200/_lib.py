@@ -35,8 +35,8 @@ class PyramidPlan(C.Structure):
 class DetectWs(C.Structure):
     _fields_ = [
         ("B", C.c_int), ("cand_cap", C.c_int), ("n_level_slots", C.c_int),
-        ("d_cand_val", C.c_void_p), ("d_cand_seq", C.c_void_p), ("d_cand_scyx", C.c_void_p),
-        ("d_cand_count", C.c_void_p), ("d_level_pos", C.c_void_p), ("d_level_emit", C.c_void_p),
+        ("d_cand_val", C.c_void_p), ("d_cand_seq", C.c_void_p), ("d_cand_scyx", C.c_void_p), ("d_cand_aux", C.c_void_p),
+        ("d_cand_count", C.c_void_p), ("d_level_pos", C.c_void_p), ("d_level_emit", C.c_void_p), ("d_variants", C.c_void_p),
         ("d_octave_maps", C.c_void_p),
     ]
 

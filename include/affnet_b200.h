@@ -90,11 +90,13 @@ typedef struct {
     int n_level_slots;         /* n_octaves * (n_levels-2) detection levels */
     /* device buffers, caller-allocated (sizes in elements) */
     float* d_cand_val;         /* [B, cand_cap]   response after octave-map masking (may be negative, Q4) */
-    uint32_t* d_cand_seq;      /* [B, cand_cap]   (level_slot << 27) | flat pixel index */
+    uint32_t* d_cand_seq;      /* [B, cand_cap]   (level_slot << 27) | flat pixel index; 0xFFFFFFFF = dropped */
     float* d_cand_scyx;        /* [B, cand_cap, 3] normalised (scale, y, x) */
+    float* d_cand_aux;         /* [B, cand_cap, 2] raw NMS value of the same pixel at the octave's detection levels 1 and 2 */
     int* d_cand_count;         /* [B]             number appended (may exceed cand_cap -> overflow) */
     int* d_level_pos;          /* [B, n_level_slots] count of responses > 0 at each detection level */
     int* d_level_emit;         /* [B, n_level_slots] count of non-zero responses at each level */
+    int* d_variants;           /* [B, n_octaves, 16] acceptance-hypothesis counters of the fused detector */
     uint8_t* d_octave_maps;    /* [4 * B * sum_o h_o*w_o] scratch for the octave maps (uint8, Q4 semantics) */
 } ag_detect_ws_t;
 
