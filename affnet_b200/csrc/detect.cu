@@ -11,6 +11,8 @@
 // because every float op that decides survival is done in the reference's order with explicit
 // non-contracted intrinsics (__fmul_rn/__fsub_rn/__fadd_rn): the Hessian determinant, `(x - max) + 1e-5 > 0`,
 // `resp * (1 - octaveMap)` and the float->uint8 wrap of the octave map (Q4).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ag {
@@ -417,6 +419,207 @@ __global__ void __launch_bounds__(DNT) detect_fused_kernel(const FusedParams P) 
     }
 }
 
+
+// ======================================================================================================================
+// Register-resident formulation of the fused detector: one warp owns a band of rows of a 30-column strip (32 lanes = 30
+// output columns + one response-halo column each side), walks down the rows keeping three pyramid rows of all five levels
+// in registers, takes horizontal neighbours by warp shuffle, and never touches shared memory on the common path:
+//   per pixel and level: 1 coalesced load + 2 shuffles + the Hessian; separable 3x3 max via 2 shuffles + FMNMX3.
+// Candidates (about 1 % of the pixels) take a warp-cooperative slow path that gathers the 3x3x3 response neighbourhood by
+// shuffle for the soft-argmax.  Semantics are identical to detect_fused_kernel (same hypothesis counters, same records).
+// ======================================================================================================================
+constexpr int WCOLS = 30;   // output columns per warp strip
+constexpr int WROWS = 32;   // output rows per warp band
+constexpr int WNT = 128;    // 4 warps per CTA, one band each
+
+struct WarpOctave {
+    const float* lvl[5];
+    float s4[5], sc[5];
+    int h, w, strips_x, bands_y, unit_base;   // unit = (band, strip)
+};
+struct WarpParams {
+    WarpOctave oct[AG_MAX_OCTAVES];
+    int n_oct, total_units;
+    float th;
+    int mr_border, cand_cap;
+    float* cand_val;
+    float* cand_aux;
+    uint32_t* cand_seq;
+    float* cand_scyx;
+    int* cand_count;
+    int* variants;
+};
+
+__device__ __forceinline__ float hessian_regs(float tl, float tc, float tr, float ml, float mc, float mr, float bl, float bc, float br, float s4, float th) {
+    const float gxx = __fadd_rn(__fsub_rn(ml, __fmul_rn(2.0f, mc)), mr);
+    const float gyy = __fadd_rn(__fsub_rn(tc, __fmul_rn(2.0f, mc)), bc);
+    const float gxa = __fsub_rn(__fmul_rn(0.5f, tl), __fmul_rn(0.5f, tr));
+    const float gxb = __fsub_rn(__fmul_rn(0.5f, bl), __fmul_rn(0.5f, br));
+    const float gxy = __fsub_rn(__fmul_rn(0.5f, gxa), __fmul_rn(0.5f, gxb));
+    const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));
+    return fmaxf(__fsub_rn(__fmul_rn(fabsf(det), s4), th), 0.0f);
+}
+
+__global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
+    const int lane = threadIdx.x & 31;
+    int u = blockIdx.x * (WNT / 32) + (threadIdx.x >> 5);
+    if (u >= P.total_units) return;
+    int oi = 0;
+#pragma unroll 1
+    for (int i = 1; i < P.n_oct; i++)
+        if (u >= P.oct[i].unit_base) oi = i;
+    const WarpOctave& O = P.oct[oi];
+    u -= O.unit_base;
+    const int b = blockIdx.y, h = O.h, w = O.w;
+    const int band = u / O.strips_x, strip = u - band * O.strips_x;
+    const int r0 = band * WROWS;                       // first output row
+    const int gx = strip * WCOLS - 1 + lane;           // this lane's column (lanes 0 and 31 are response halo)
+    const bool col_in = gx >= 0 && gx < w;
+    const int cx = clampi(gx, 0, w - 1), cxl = clampi(gx - 1, 0, w - 1), cxr = clampi(gx + 1, 0, w - 1);
+    const size_t img_off = (size_t)b * h * w;
+    const bool border_ok = (P.mr_border < w) && (P.mr_border < h);
+    const bool own = lane >= 1 && lane <= WCOLS && col_in;   // lanes that own an output column
+    const bool col_ok = own && border_ok && gx >= P.mr_border && gx < w - P.mr_border;
+
+    // pyramid rows (left, centre, right) of the three most recent rows, five levels: index [d][row slot]
+    float pl[5][3], pc[5][3], pr[5][3];
+    float rs[5][3];      // responses of the three most recent response rows
+    float rmx[5][3];     // horizontal 3-max of those rows
+    int var[14];
+#pragma unroll
+    for (int i = 0; i < 14; i++) var[i] = 0;
+
+    auto load_row = [&](int y, int slot) {
+        const int cy = clampi(y, 0, h - 1);
+#pragma unroll
+        for (int d = 0; d < 5; d++) {
+            const float* rowp = O.lvl[d] + img_off + (size_t)cy * w;
+            const float c = __ldg(rowp + cx);
+            // neighbours: shuffles inside the strip, direct (clamped) loads on the two edge lanes
+            float l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
+            if (lane == 0) l = __ldg(rowp + cxl);
+            if (lane == 31) r = __ldg(rowp + cxr);
+            pl[d][slot] = l; pc[d][slot] = c; pr[d][slot] = r;
+        }
+    };
+    // response row y from pyramid rows y-1,y,y+1 held in slots (a,b,c); zero outside the image
+    auto resp_row = [&](int y, int a, int bq, int c, int slot) {
+        const bool in = col_in && y >= 0 && y < h;
+#pragma unroll
+        for (int d = 0; d < 5; d++) {
+            const float r = in ? hessian_regs(pl[d][a], pc[d][a], pr[d][a], pl[d][bq], pc[d][bq], pr[d][bq], pl[d][c], pc[d][c], pr[d][c], O.s4[d], P.th) : 0.f;
+            rs[d][slot] = r;
+            const float l = __shfl_up_sync(0xffffffffu, r, 1), rr = __shfl_down_sync(0xffffffffu, r, 1);
+            rmx[d][slot] = fmaxf(fmaxf(lane > 0 ? l : 0.f, r), lane < 31 ? rr : 0.f);
+        }
+    };
+
+    // prologue: pyramid rows r0-2, r0-1, r0 -> response row r0-1; then r0+1 -> response row r0
+    load_row(r0 - 2, 0); load_row(r0 - 1, 1); load_row(r0, 2);
+    resp_row(r0 - 1, 0, 1, 2, 0);
+    load_row(r0 + 1, 0);
+    resp_row(r0, 1, 2, 0, 1);
+    const int r_end = min(r0 + WROWS, h);
+    const float min_size = (float)min(h, w);
+#pragma unroll 1
+    for (int y = r0; y < r_end; y++) {
+        // invariant (k = y - r0): pyramid rows y-1,y,y+1 live in slots (k+1)%3,(k+2)%3,k%3; response rows y-1,y in k%3,(k+1)%3
+        const int k = (y - r0) % 3;
+        const int sa = (k + 1) % 3, sb = (k + 2) % 3, sc3 = k;   // pyramid slots of rows y-1, y, y+1
+        // next pyramid row y+2 overwrites the slot of row y-1, then response row y+1 from rows y, y+1, y+2
+        // (static slot indices via a 3-way switch keep everything in registers)
+        if (k == 0) { load_row(y + 2, 1); resp_row(y + 1, 2, 0, 1, 2); }
+        else if (k == 1) { load_row(y + 2, 2); resp_row(y + 1, 0, 1, 2, 0); }
+        else { load_row(y + 2, 0); resp_row(y + 1, 1, 2, 0, 1); }
+        (void)sa; (void)sb; (void)sc3;
+        // response rows y-1, y, y+1 are now in slots k, (k+1)%3, (k+2)%3
+        float n1 = 0.f, n2 = 0.f, n3 = 0.f;
+        float M[5], xc[3];
+#pragma unroll
+        for (int d = 0; d < 5; d++) M[d] = fmaxf(fmaxf(rmx[d][0], rmx[d][1]), rmx[d][2]);
+        if (k == 0) { xc[0] = rs[1][1]; xc[1] = rs[2][1]; xc[2] = rs[3][1]; }
+        else if (k == 1) { xc[0] = rs[1][2]; xc[1] = rs[2][2]; xc[2] = rs[3][2]; }
+        else { xc[0] = rs[1][0]; xc[1] = rs[2][0]; xc[2] = rs[3][0]; }
+        const bool row_ok = col_ok && y >= P.mr_border && y < h - P.mr_border;
+        if (row_ok) {
+            n1 = (__fadd_rn(__fsub_rn(xc[0], fmaxf(fmaxf(M[0], M[1]), M[2])), 1e-5f) > 0.f) ? xc[0] : 0.f;
+            n2 = (__fadd_rn(__fsub_rn(xc[1], fmaxf(fmaxf(M[1], M[2]), M[3])), 1e-5f) > 0.f) ? xc[1] : 0.f;
+            n3 = (__fadd_rn(__fsub_rn(xc[2], fmaxf(fmaxf(M[2], M[3]), M[4])), 1e-5f) > 0.f) ? xc[2] : 0.f;
+        }
+        const bool cand = (n1 != 0.f) || (n2 != 0.f) || (n3 != 0.f);
+        unsigned todo = __ballot_sync(0xffffffffu, cand);
+        if (todo == 0) continue;
+        if (cand) {
+            var[0] += n1 > 0.f; var[7] += n1 != 0.f;
+#pragma unroll
+            for (int a1 = 0; a1 < 2; a1++) {
+                const uint8_t om1 = a1 ? om_after(0, n1) : (uint8_t)0;
+                const float v2 = masked(n2, om1);
+                var[1 + a1] += v2 > 0.f; var[8 + a1] += v2 != 0.f;
+#pragma unroll
+                for (int a2 = 0; a2 < 2; a2++) {
+                    const uint8_t om2 = a2 ? om_after(om1, v2) : om1;
+                    const float v3 = masked(n3, om2);
+                    var[3 + a1 * 2 + a2] += v3 > 0.f; var[10 + a1 * 2 + a2] += v3 != 0.f;
+                }
+            }
+        }
+        // slow path: for each candidate lane, every lane helps to gather the 3x3 response neighbourhood of the five levels
+        while (todo) {
+            const int L = __ffs(todo) - 1;
+            todo &= todo - 1;
+            // neighbourhood sums for the soft-argmax of levels q = 0..2 (response levels q..q+2): gathered per level d, row slot
+            float S[5], SY[5], SX[5];   // per level: sum r, sum off_y*r, sum off_x*r over the 3x3 window
+#pragma unroll
+            for (int d = 0; d < 5; d++) {
+                float s = 0.f, sy = 0.f, sx = 0.f;
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++) {
+                    // row slot of response row (y - 1 + rr)
+                    const float v = (k == 0) ? rs[d][rr] : (k == 1) ? rs[d][(rr + 1) % 3] : rs[d][(rr + 2) % 3];
+                    const float a = __shfl_sync(0xffffffffu, v, (L + 31) & 31), c = __shfl_sync(0xffffffffu, v, L), e = __shfl_sync(0xffffffffu, v, (L + 1) & 31);
+                    // conv2d order (dy outer, dx inner) with fmaf accumulation as in the tiled kernel
+                    const float oy = -0.5f + (float)rr;
+                    s += a; sy = fmaf(oy, a, sy); sx = fmaf(-0.5f, a, sx);
+                    s += c; sy = fmaf(oy, c, sy); sx = fmaf(0.5f, c, sx);
+                    s += e; sy = fmaf(oy, e, sy); sx = fmaf(1.5f, e, sx);
+                }
+                S[d] = s; SY[d] = sy; SX[d] = sx;
+            }
+            if (lane == L) {
+                const float nn[3] = {n1, n2, n3};
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    if (nn[q] == 0.f) continue;
+                    const int dst = atomicAdd(&P.cand_count[b], 1);
+                    if (dst < P.cand_cap) {
+                        float ns = 0.f, ny = 0.f, nx = 0.f, den = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 3; d++) { ns = fmaf(O.sc[q + d], S[q + d], ns); ny += SY[q + d]; nx += SX[q + d]; den += S[q + d]; }
+                        den = __fadd_rn(den, 1e-8f);
+                        const size_t o = (size_t)b * P.cand_cap + dst;
+                        P.cand_val[o] = nn[q];
+                        P.cand_aux[o * 2 + 0] = n1;
+                        P.cand_aux[o * 2 + 1] = n2;
+                        P.cand_seq[o] = ((uint32_t)(oi * 3 + q) << SEQ_PIX_BITS) | (uint32_t)(y * w + gx);
+                        P.cand_scyx[o * 3 + 0] = __fdiv_rn(__fdiv_rn(ns, den), min_size);
+                        P.cand_scyx[o * 3 + 1] = __fdiv_rn(__fadd_rn(__fdiv_rn(ny, den), (float)y), (float)h);
+                        P.cand_scyx[o * 3 + 2] = __fdiv_rn(__fadd_rn(__fdiv_rn(nx, den), (float)gx), (float)w);
+                    }
+                }
+            }
+        }
+    }
+    // hypothesis counters: warp reduce, one atomic per non-zero counter
+#pragma unroll
+    for (int i = 0; i < 14; i++) {
+        int v = var[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&P.variants[((size_t)b * P.n_oct + oi) * NVAR + i], v);
+    }
+}
+
 // Picks the hypothesis branch the counters select, fills level_pos / level_emit, and turns every candidate's raw NMS value
 // into the reference's masked response (or invalidates it: slot 31 is never accepted).
 __global__ void resolve_kernel(const int* __restrict__ variants, int n_oct, int cand_cap, const int* __restrict__ cand_count,
@@ -701,6 +904,30 @@ int ag_detect(const ag_pyramid_plan_t* p, const float* d_pyr, float th, int mr_b
             tiles += O.tiles_x * O.tiles_y;
         }
         F.total_tiles = tiles;
+        static const bool use_tiled = getenv("AG_DETECT_TILED") != nullptr;   // A/B switch: shared-memory tiled variant
+        if (!use_tiled) {
+            WarpParams Wp;
+            memset(&Wp, 0, sizeof(Wp));
+            Wp.n_oct = p->n_octaves; Wp.th = th; Wp.mr_border = mr_border; Wp.cand_cap = ws->cand_cap;
+            Wp.cand_val = ws->d_cand_val; Wp.cand_aux = ws->d_cand_aux; Wp.cand_seq = ws->d_cand_seq; Wp.cand_scyx = ws->d_cand_scyx;
+            Wp.cand_count = ws->d_cand_count; Wp.variants = ws->d_variants;
+            int units = 0;
+            for (int o = 0; o < p->n_octaves; o++) {
+                WarpOctave& O = Wp.oct[o];
+                for (int d = 0; d < 5; d++) { O.lvl[d] = F.oct[o].lvl[d]; O.s4[d] = F.oct[o].s4[d]; O.sc[d] = F.oct[o].sc[d]; }
+                O.h = p->h[o]; O.w = p->w[o];
+                O.strips_x = cdiv(O.w, WCOLS); O.bands_y = cdiv(O.h, WROWS);
+                O.unit_base = units;
+                units += O.strips_x * O.bands_y;
+            }
+            Wp.total_units = units;
+            detect_warp_kernel<<<dim3(cdiv(units, WNT / 32), p->B), WNT, 0, st>>>(Wp);
+            AG_CHECK_LAUNCH("detect_warp_kernel");
+            resolve_kernel<<<dim3(8, p->B), 256, 0, st>>>(ws->d_variants, p->n_octaves, ws->cand_cap, ws->d_cand_count, ws->d_cand_val, ws->d_cand_aux,
+                                                           ws->d_cand_seq, ws->d_level_pos, ws->d_level_emit);
+            AG_CHECK_LAUNCH("resolve_kernel");
+            return AG_OK;
+        }
         constexpr size_t fsmem = sizeof(float) * (5 * PW * (PW + 1) + 5 * RW * (RW + 1));
         static bool configured = false;
         if (!configured) {
