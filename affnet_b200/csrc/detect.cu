@@ -13,6 +13,8 @@
 // `resp * (1 - octaveMap)` and the float->uint8 wrap of the octave map (Q4).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ag {
@@ -460,9 +462,21 @@ __device__ __forceinline__ float hessian_regs(float tl, float tc, float tr, floa
     return fmaxf(__fsub_rn(__fmul_rn(fabsf(det), s4), th), 0.0f);
 }
 
+constexpr int WRING = 8;   // ring of pyramid rows per warp (cp.async prefetch distance WPD, 3 rows live)
+constexpr int WPD = 5;
+constexpr int WROWLEN = 34;  // 32 lane columns + one extra column each side
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+template <int S0, int S1, int S2>   // response slots holding rows y-1, y, y+1
+struct Slots {};
+
 __global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
-    const int lane = threadIdx.x & 31;
-    int u = blockIdx.x * (WNT / 32) + (threadIdx.x >> 5);
+    __shared__ float s_ring[WNT / 32][WRING][5][WROWLEN];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int u = blockIdx.x * (WNT / 32) + wib;
     if (u >= P.total_units) return;
     int oi = 0;
 #pragma unroll 1
@@ -472,83 +486,72 @@ __global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
     u -= O.unit_base;
     const int b = blockIdx.y, h = O.h, w = O.w;
     const int band = u / O.strips_x, strip = u - band * O.strips_x;
-    const int r0 = band * WROWS;                       // first output row
-    const int gx = strip * WCOLS - 1 + lane;           // this lane's column (lanes 0 and 31 are response halo)
+    const int r0 = band * WROWS;
+    const int gx = strip * WCOLS - 1 + lane;            // lane's column; lanes 0 / 31 are the response halo
     const bool col_in = gx >= 0 && gx < w;
     const int cx = clampi(gx, 0, w - 1), cxl = clampi(gx - 1, 0, w - 1), cxr = clampi(gx + 1, 0, w - 1);
     const size_t img_off = (size_t)b * h * w;
     const bool border_ok = (P.mr_border < w) && (P.mr_border < h);
-    const bool own = lane >= 1 && lane <= WCOLS && col_in;   // lanes that own an output column
-    const bool col_ok = own && border_ok && gx >= P.mr_border && gx < w - P.mr_border;
+    const bool col_ok = lane >= 1 && lane <= WCOLS && col_in && border_ok && gx >= P.mr_border && gx < w - P.mr_border;
+    const int rows_out = min(WROWS, h - r0);
+    const int n_rows = rows_out + 4;                     // pyramid rows r0-2 .. r0+rows_out+1
+    float (*ring)[5][WROWLEN] = s_ring[wib];
 
-    // pyramid rows (left, centre, right) of the three most recent rows, five levels: index [d][row slot]
-    float pl[5][3], pc[5][3], pr[5][3];
-    float rs[5][3];      // responses of the three most recent response rows
-    float rmx[5][3];     // horizontal 3-max of those rows
+    auto issue_row = [&](int c) {                        // pyramid row r0-2+c -> ring slot c % WRING (replicate-clamped)
+        if (c < n_rows) {
+            const int cy = clampi(r0 - 2 + c, 0, h - 1);
+#pragma unroll
+            for (int d = 0; d < 5; d++) {
+                const float* rowp = O.lvl[d] + img_off + (size_t)cy * w;
+                float* dst = ring[c % WRING][d];
+                cp_async4(dst + lane + 1, rowp + cx);
+                if (lane == 0) cp_async4(dst, rowp + cxl);
+                if (lane == 31) cp_async4(dst + 33, rowp + cxr);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float rs[5][3], rmx[5][3];
     int var[14];
 #pragma unroll
     for (int i = 0; i < 14; i++) var[i] = 0;
-
-    auto load_row = [&](int y, int slot) {
-        const int cy = clampi(y, 0, h - 1);
-#pragma unroll
-        for (int d = 0; d < 5; d++) {
-            const float* rowp = O.lvl[d] + img_off + (size_t)cy * w;
-            const float c = __ldg(rowp + cx);
-            // neighbours: shuffles inside the strip, direct (clamped) loads on the two edge lanes
-            float l = __shfl_up_sync(0xffffffffu, c, 1), r = __shfl_down_sync(0xffffffffu, c, 1);
-            if (lane == 0) l = __ldg(rowp + cxl);
-            if (lane == 31) r = __ldg(rowp + cxr);
-            pl[d][slot] = l; pc[d][slot] = c; pr[d][slot] = r;
-        }
-    };
-    // response row y from pyramid rows y-1,y,y+1 held in slots (a,b,c); zero outside the image
-    auto resp_row = [&](int y, int a, int bq, int c, int slot) {
-        const bool in = col_in && y >= 0 && y < h;
-#pragma unroll
-        for (int d = 0; d < 5; d++) {
-            const float r = in ? hessian_regs(pl[d][a], pc[d][a], pr[d][a], pl[d][bq], pc[d][bq], pr[d][bq], pl[d][c], pc[d][c], pr[d][c], O.s4[d], P.th) : 0.f;
-            rs[d][slot] = r;
-            const float l = __shfl_up_sync(0xffffffffu, r, 1), rr = __shfl_down_sync(0xffffffffu, r, 1);
-            rmx[d][slot] = fmaxf(fmaxf(lane > 0 ? l : 0.f, r), lane < 31 ? rr : 0.f);
-        }
-    };
-
-    // prologue: pyramid rows r0-2, r0-1, r0 -> response row r0-1; then r0+1 -> response row r0
-    load_row(r0 - 2, 0); load_row(r0 - 1, 1); load_row(r0, 2);
-    resp_row(r0 - 1, 0, 1, 2, 0);
-    load_row(r0 + 1, 0);
-    resp_row(r0, 1, 2, 0, 1);
-    const int r_end = min(r0 + WROWS, h);
     const float min_size = (float)min(h, w);
-#pragma unroll 1
-    for (int y = r0; y < r_end; y++) {
-        // invariant (k = y - r0): pyramid rows y-1,y,y+1 live in slots (k+1)%3,(k+2)%3,k%3; response rows y-1,y in k%3,(k+1)%3
-        const int k = (y - r0) % 3;
-        const int sa = (k + 1) % 3, sb = (k + 2) % 3, sc3 = k;   // pyramid slots of rows y-1, y, y+1
-        // next pyramid row y+2 overwrites the slot of row y-1, then response row y+1 from rows y, y+1, y+2
-        // (static slot indices via a 3-way switch keep everything in registers)
-        if (k == 0) { load_row(y + 2, 1); resp_row(y + 1, 2, 0, 1, 2); }
-        else if (k == 1) { load_row(y + 2, 2); resp_row(y + 1, 0, 1, 2, 0); }
-        else { load_row(y + 2, 0); resp_row(y + 1, 1, 2, 0, 1); }
-        (void)sa; (void)sb; (void)sc3;
-        // response rows y-1, y, y+1 are now in slots k, (k+1)%3, (k+2)%3
-        float n1 = 0.f, n2 = 0.f, n3 = 0.f;
-        float M[5], xc[3];
+
+    // response row (image row yy) from ring rows c-2, c-1, c into response slot SL
+    auto resp_row = [&](int c, int yy, auto SLc) {
+        constexpr int SL = decltype(SLc)::value;
+        const bool in = col_in && yy >= 0 && yy < h;
+        const float (*t)[WROWLEN] = ring[(c - 2) % WRING];
+        const float (*m)[WROWLEN] = ring[(c - 1) % WRING];
+        const float (*bt)[WROWLEN] = ring[c % WRING];
 #pragma unroll
-        for (int d = 0; d < 5; d++) M[d] = fmaxf(fmaxf(rmx[d][0], rmx[d][1]), rmx[d][2]);
-        if (k == 0) { xc[0] = rs[1][1]; xc[1] = rs[2][1]; xc[2] = rs[3][1]; }
-        else if (k == 1) { xc[0] = rs[1][2]; xc[1] = rs[2][2]; xc[2] = rs[3][2]; }
-        else { xc[0] = rs[1][0]; xc[1] = rs[2][0]; xc[2] = rs[3][0]; }
-        const bool row_ok = col_ok && y >= P.mr_border && y < h - P.mr_border;
-        if (row_ok) {
-            n1 = (__fadd_rn(__fsub_rn(xc[0], fmaxf(fmaxf(M[0], M[1]), M[2])), 1e-5f) > 0.f) ? xc[0] : 0.f;
-            n2 = (__fadd_rn(__fsub_rn(xc[1], fmaxf(fmaxf(M[1], M[2]), M[3])), 1e-5f) > 0.f) ? xc[1] : 0.f;
-            n3 = (__fadd_rn(__fsub_rn(xc[2], fmaxf(fmaxf(M[2], M[3]), M[4])), 1e-5f) > 0.f) ? xc[2] : 0.f;
+        for (int d = 0; d < 5; d++) {
+            float r = 0.f;
+            if (in) r = hessian_regs(t[d][lane], t[d][lane + 1], t[d][lane + 2], m[d][lane], m[d][lane + 1], m[d][lane + 2], bt[d][lane], bt[d][lane + 1],
+                                     bt[d][lane + 2], O.s4[d], P.th);
+            rs[d][SL] = r;
+            const float l = __shfl_up_sync(0xffffffffu, r, 1), rr = __shfl_down_sync(0xffffffffu, r, 1);
+            rmx[d][SL] = fmaxf(fmaxf(lane > 0 ? l : 0.f, r), lane < 31 ? rr : 0.f);
+        }
+    };
+
+    // NMS + candidate handling for output row y; response rows y-1, y, y+1 are in slots A, B, C
+    auto nms_row = [&](int y, auto Ac, auto Bc, auto Cc) {
+        constexpr int A = decltype(Ac)::value, Bq = decltype(Bc)::value, Cq = decltype(Cc)::value;
+        float n1 = 0.f, n2 = 0.f, n3 = 0.f;
+        if (col_ok && y >= P.mr_border && y < h - P.mr_border) {
+            float M[5];
+#pragma unroll
+            for (int d = 0; d < 5; d++) M[d] = fmaxf(fmaxf(rmx[d][A], rmx[d][Bq]), rmx[d][Cq]);
+            const float x1 = rs[1][Bq], x2 = rs[2][Bq], x3 = rs[3][Bq];
+            n1 = (__fadd_rn(__fsub_rn(x1, fmaxf(fmaxf(M[0], M[1]), M[2])), 1e-5f) > 0.f) ? x1 : 0.f;   // NMS3d, HandCraftedModules.py:220
+            n2 = (__fadd_rn(__fsub_rn(x2, fmaxf(fmaxf(M[1], M[2]), M[3])), 1e-5f) > 0.f) ? x2 : 0.f;
+            n3 = (__fadd_rn(__fsub_rn(x3, fmaxf(fmaxf(M[2], M[3]), M[4])), 1e-5f) > 0.f) ? x3 : 0.f;
         }
         const bool cand = (n1 != 0.f) || (n2 != 0.f) || (n3 != 0.f);
         unsigned todo = __ballot_sync(0xffffffffu, cand);
-        if (todo == 0) continue;
+        if (todo == 0) return;
         if (cand) {
             var[0] += n1 > 0.f; var[7] += n1 != 0.f;
 #pragma unroll
@@ -564,27 +567,23 @@ __global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
                 }
             }
         }
-        // slow path: for each candidate lane, every lane helps to gather the 3x3 response neighbourhood of the five levels
-        while (todo) {
+        while (todo) {   // warp-cooperative soft-argmax of one candidate lane (HandCraftedModules.py:266-290)
             const int L = __ffs(todo) - 1;
             todo &= todo - 1;
-            // neighbourhood sums for the soft-argmax of levels q = 0..2 (response levels q..q+2): gathered per level d, row slot
-            float S[5], SY[5], SX[5];   // per level: sum r, sum off_y*r, sum off_x*r over the 3x3 window
+            float S[5], SY[5], SX[5];
 #pragma unroll
             for (int d = 0; d < 5; d++) {
-                float s = 0.f, sy = 0.f, sx = 0.f;
+                float sm = 0.f, sy = 0.f, sx = 0.f;
 #pragma unroll
                 for (int rr = 0; rr < 3; rr++) {
-                    // row slot of response row (y - 1 + rr)
-                    const float v = (k == 0) ? rs[d][rr] : (k == 1) ? rs[d][(rr + 1) % 3] : rs[d][(rr + 2) % 3];
+                    const float v = rr == 0 ? rs[d][A] : rr == 1 ? rs[d][Bq] : rs[d][Cq];
                     const float a = __shfl_sync(0xffffffffu, v, (L + 31) & 31), c = __shfl_sync(0xffffffffu, v, L), e = __shfl_sync(0xffffffffu, v, (L + 1) & 31);
-                    // conv2d order (dy outer, dx inner) with fmaf accumulation as in the tiled kernel
                     const float oy = -0.5f + (float)rr;
-                    s += a; sy = fmaf(oy, a, sy); sx = fmaf(-0.5f, a, sx);
-                    s += c; sy = fmaf(oy, c, sy); sx = fmaf(0.5f, c, sx);
-                    s += e; sy = fmaf(oy, e, sy); sx = fmaf(1.5f, e, sx);
+                    sm += a; sy = fmaf(oy, a, sy); sx = fmaf(-0.5f, a, sx);
+                    sm += c; sy = fmaf(oy, c, sy); sx = fmaf(0.5f, c, sx);
+                    sm += e; sy = fmaf(oy, e, sy); sx = fmaf(1.5f, e, sx);
                 }
-                S[d] = s; SY[d] = sy; SX[d] = sx;
+                S[d] = sm; SY[d] = sy; SX[d] = sx;
             }
             if (lane == L) {
                 const float nn[3] = {n1, n2, n3};
@@ -609,8 +608,29 @@ __global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
                 }
             }
         }
+    };
+
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+#pragma unroll 1
+    for (int c = 0; c < WPD; c++) issue_row(c);
+    // consume pyramid row c: response row j = c-2 (image row r0-3+c) goes to slot j%3; output row y = r0+c-4
+#pragma unroll 1
+    for (int c = 0; c < n_rows; c++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(WPD - 1) : "memory");
+        __syncwarp();
+        if (c >= 2) {
+            const int j = c - 2, yy = r0 - 3 + c, y = r0 + c - 4;
+            const int js = j % 3;
+            if (js == 0) { resp_row(c, yy, I0{}); if (c >= 4) nms_row(y, I1{}, I2{}, I0{}); }
+            else if (js == 1) { resp_row(c, yy, I1{}); if (c >= 4) nms_row(y, I2{}, I0{}, I1{}); }
+            else { resp_row(c, yy, I2{}); if (c >= 4) nms_row(y, I0{}, I1{}, I2{}); }
+        }
+        __syncwarp();            // every lane has finished reading ring rows <= c before slot (c+WPD)%WRING is refilled
+        issue_row(c + WPD);
     }
-    // hypothesis counters: warp reduce, one atomic per non-zero counter
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 14; i++) {
         int v = var[i];
