@@ -465,6 +465,7 @@ __device__ __forceinline__ float hessian_regs(float tl, float tc, float tr, floa
 constexpr int WRING = 8;   // ring of pyramid rows per warp (cp.async prefetch distance WPD, 3 rows live)
 constexpr int WPD = 5;
 constexpr int WROWLEN = 34;  // 32 lane columns + one extra column each side
+constexpr int WCBUF = 96;    // staged candidates per warp (a row yields at most 90); flushed with ONE atomic
 
 __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
@@ -475,6 +476,7 @@ struct Slots {};
 
 __global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
     __shared__ float s_ring[WNT / 32][WRING][5][WROWLEN];
+    __shared__ float s_cbuf[WNT / 32][7][WCBUF];   // per-warp candidate staging: val, aux0, aux1, seq, sc, y, x
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int u = blockIdx.x * (WNT / 32) + wib;
     if (u >= P.total_units) return;
@@ -518,6 +520,31 @@ __global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
     for (int i = 0; i < 14; i++) var[i] = 0;
     const float min_size = (float)min(h, w);
 
+    int buf_n = 0;   // warp-uniform
+    float (*cbuf)[WCBUF] = s_cbuf[wib];
+    auto flush = [&]() {
+        if (buf_n == 0) return;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&P.cand_count[b], buf_n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (int i = lane; i < buf_n; i += 32) {
+            const int dst = base + i;
+            if (dst < P.cand_cap) {
+                const size_t o = (size_t)b * P.cand_cap + dst;
+                P.cand_val[o] = cbuf[0][i];
+                P.cand_aux[o * 2 + 0] = cbuf[1][i];
+                P.cand_aux[o * 2 + 1] = cbuf[2][i];
+                P.cand_seq[o] = __float_as_uint(cbuf[3][i]);
+                P.cand_scyx[o * 3 + 0] = cbuf[4][i];
+                P.cand_scyx[o * 3 + 1] = cbuf[5][i];
+                P.cand_scyx[o * 3 + 2] = cbuf[6][i];
+            }
+        }
+        __syncwarp();
+        buf_n = 0;
+    };
+
     // response row (image row yy) from ring rows c-2, c-1, c into response slot SL
     auto resp_row = [&](int c, int yy, auto SLc) {
         constexpr int SL = decltype(SLc)::value;
@@ -552,6 +579,9 @@ __global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
         const bool cand = (n1 != 0.f) || (n2 != 0.f) || (n3 != 0.f);
         unsigned todo = __ballot_sync(0xffffffffu, cand);
         if (todo == 0) return;
+        const int row_total = __popc(__ballot_sync(0xffffffffu, n1 != 0.f)) + __popc(__ballot_sync(0xffffffffu, n2 != 0.f)) +
+                              __popc(__ballot_sync(0xffffffffu, n3 != 0.f));
+        if (buf_n + row_total > WCBUF) flush();
         if (cand) {
             var[0] += n1 > 0.f; var[7] += n1 != 0.f;
 #pragma unroll
@@ -585,28 +615,28 @@ __global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
                 }
                 S[d] = sm; SY[d] = sy; SX[d] = sx;
             }
+            const int kL = __shfl_sync(0xffffffffu, (int)(n1 != 0.f) + (int)(n2 != 0.f) + (int)(n3 != 0.f), L);
             if (lane == L) {
                 const float nn[3] = {n1, n2, n3};
+                int dst = buf_n;
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
                     if (nn[q] == 0.f) continue;
-                    const int dst = atomicAdd(&P.cand_count[b], 1);
-                    if (dst < P.cand_cap) {
-                        float ns = 0.f, ny = 0.f, nx = 0.f, den = 0.f;
+                    float ns = 0.f, ny = 0.f, nx = 0.f, den = 0.f;
 #pragma unroll
-                        for (int d = 0; d < 3; d++) { ns = fmaf(O.sc[q + d], S[q + d], ns); ny += SY[q + d]; nx += SX[q + d]; den += S[q + d]; }
-                        den = __fadd_rn(den, 1e-8f);
-                        const size_t o = (size_t)b * P.cand_cap + dst;
-                        P.cand_val[o] = nn[q];
-                        P.cand_aux[o * 2 + 0] = n1;
-                        P.cand_aux[o * 2 + 1] = n2;
-                        P.cand_seq[o] = ((uint32_t)(oi * 3 + q) << SEQ_PIX_BITS) | (uint32_t)(y * w + gx);
-                        P.cand_scyx[o * 3 + 0] = __fdiv_rn(__fdiv_rn(ns, den), min_size);
-                        P.cand_scyx[o * 3 + 1] = __fdiv_rn(__fadd_rn(__fdiv_rn(ny, den), (float)y), (float)h);
-                        P.cand_scyx[o * 3 + 2] = __fdiv_rn(__fadd_rn(__fdiv_rn(nx, den), (float)gx), (float)w);
-                    }
+                    for (int d = 0; d < 3; d++) { ns = fmaf(O.sc[q + d], S[q + d], ns); ny += SY[q + d]; nx += SX[q + d]; den += S[q + d]; }
+                    den = __fadd_rn(den, 1e-8f);
+                    cbuf[0][dst] = nn[q];
+                    cbuf[1][dst] = n1;
+                    cbuf[2][dst] = n2;
+                    cbuf[3][dst] = __uint_as_float(((uint32_t)(oi * 3 + q) << SEQ_PIX_BITS) | (uint32_t)(y * w + gx));
+                    cbuf[4][dst] = __fdiv_rn(__fdiv_rn(ns, den), min_size);
+                    cbuf[5][dst] = __fdiv_rn(__fadd_rn(__fdiv_rn(ny, den), (float)y), (float)h);
+                    cbuf[6][dst] = __fdiv_rn(__fadd_rn(__fdiv_rn(nx, den), (float)gx), (float)w);
+                    dst++;
                 }
             }
+            buf_n += kL;
         }
     };
 
@@ -631,6 +661,7 @@ __global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
         issue_row(c + WPD);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    flush();
 #pragma unroll
     for (int i = 0; i < 14; i++) {
         int v = var[i];
