@@ -514,7 +514,13 @@ __global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    float rs[5][3], rmx[5][3];
+    // rotating register state of the three most recent response rows (slot 0 = oldest): response, horizontal 3-max, and the
+    // horizontal sums the soft-argmax needs (sum r, sum x_off * r), all taken from the same two shuffles
+    float rs[5][3], rmx[5][3], hs[5][3], hx[5][3];
+#pragma unroll
+    for (int d = 0; d < 5; d++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) { rs[d][q] = 0.f; rmx[d][q] = 0.f; hs[d][q] = 0.f; hx[d][q] = 0.f; }
     int var[14];
 #pragma unroll
     for (int i = 0; i < 14; i++) var[i] = 0;
@@ -545,117 +551,94 @@ __global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
         buf_n = 0;
     };
 
-    // response row (image row yy) from ring rows c-2, c-1, c into response slot SL
-    auto resp_row = [&](int c, int yy, auto SLc) {
-        constexpr int SL = decltype(SLc)::value;
-        const bool in = col_in && yy >= 0 && yy < h;
-        const float (*t)[WROWLEN] = ring[(c - 2) % WRING];
-        const float (*m)[WROWLEN] = ring[(c - 1) % WRING];
-        const float (*bt)[WROWLEN] = ring[c % WRING];
-#pragma unroll
-        for (int d = 0; d < 5; d++) {
-            float r = 0.f;
-            if (in) r = hessian_regs(t[d][lane], t[d][lane + 1], t[d][lane + 2], m[d][lane], m[d][lane + 1], m[d][lane + 2], bt[d][lane], bt[d][lane + 1],
-                                     bt[d][lane + 2], O.s4[d], P.th);
-            rs[d][SL] = r;
-            const float l = __shfl_up_sync(0xffffffffu, r, 1), rr = __shfl_down_sync(0xffffffffu, r, 1);
-            rmx[d][SL] = fmaxf(fmaxf(lane > 0 ? l : 0.f, r), lane < 31 ? rr : 0.f);
-        }
-    };
-
-    // NMS + candidate handling for output row y; response rows y-1, y, y+1 are in slots A, B, C
-    auto nms_row = [&](int y, auto Ac, auto Bc, auto Cc) {
-        constexpr int A = decltype(Ac)::value, Bq = decltype(Bc)::value, Cq = decltype(Cc)::value;
-        float n1 = 0.f, n2 = 0.f, n3 = 0.f;
-        if (col_ok && y >= P.mr_border && y < h - P.mr_border) {
-            float M[5];
-#pragma unroll
-            for (int d = 0; d < 5; d++) M[d] = fmaxf(fmaxf(rmx[d][A], rmx[d][Bq]), rmx[d][Cq]);
-            const float x1 = rs[1][Bq], x2 = rs[2][Bq], x3 = rs[3][Bq];
-            n1 = (__fadd_rn(__fsub_rn(x1, fmaxf(fmaxf(M[0], M[1]), M[2])), 1e-5f) > 0.f) ? x1 : 0.f;   // NMS3d, HandCraftedModules.py:220
-            n2 = (__fadd_rn(__fsub_rn(x2, fmaxf(fmaxf(M[1], M[2]), M[3])), 1e-5f) > 0.f) ? x2 : 0.f;
-            n3 = (__fadd_rn(__fsub_rn(x3, fmaxf(fmaxf(M[2], M[3]), M[4])), 1e-5f) > 0.f) ? x3 : 0.f;
-        }
-        const bool cand = (n1 != 0.f) || (n2 != 0.f) || (n3 != 0.f);
-        unsigned todo = __ballot_sync(0xffffffffu, cand);
-        if (todo == 0) return;
-        const int row_total = __popc(__ballot_sync(0xffffffffu, n1 != 0.f)) + __popc(__ballot_sync(0xffffffffu, n2 != 0.f)) +
-                              __popc(__ballot_sync(0xffffffffu, n3 != 0.f));
-        if (buf_n + row_total > WCBUF) flush();
-        if (cand) {
-            var[0] += n1 > 0.f; var[7] += n1 != 0.f;
-#pragma unroll
-            for (int a1 = 0; a1 < 2; a1++) {
-                const uint8_t om1 = a1 ? om_after(0, n1) : (uint8_t)0;
-                const float v2 = masked(n2, om1);
-                var[1 + a1] += v2 > 0.f; var[8 + a1] += v2 != 0.f;
-#pragma unroll
-                for (int a2 = 0; a2 < 2; a2++) {
-                    const uint8_t om2 = a2 ? om_after(om1, v2) : om1;
-                    const float v3 = masked(n3, om2);
-                    var[3 + a1 * 2 + a2] += v3 > 0.f; var[10 + a1 * 2 + a2] += v3 != 0.f;
-                }
-            }
-        }
-        while (todo) {   // warp-cooperative soft-argmax of one candidate lane (HandCraftedModules.py:266-290)
-            const int L = __ffs(todo) - 1;
-            todo &= todo - 1;
-            float S[5], SY[5], SX[5];
-#pragma unroll
-            for (int d = 0; d < 5; d++) {
-                float sm = 0.f, sy = 0.f, sx = 0.f;
-#pragma unroll
-                for (int rr = 0; rr < 3; rr++) {
-                    const float v = rr == 0 ? rs[d][A] : rr == 1 ? rs[d][Bq] : rs[d][Cq];
-                    const float a = __shfl_sync(0xffffffffu, v, (L + 31) & 31), c = __shfl_sync(0xffffffffu, v, L), e = __shfl_sync(0xffffffffu, v, (L + 1) & 31);
-                    const float oy = -0.5f + (float)rr;
-                    sm += a; sy = fmaf(oy, a, sy); sx = fmaf(-0.5f, a, sx);
-                    sm += c; sy = fmaf(oy, c, sy); sx = fmaf(0.5f, c, sx);
-                    sm += e; sy = fmaf(oy, e, sy); sx = fmaf(1.5f, e, sx);
-                }
-                S[d] = sm; SY[d] = sy; SX[d] = sx;
-            }
-            const int kL = __shfl_sync(0xffffffffu, (int)(n1 != 0.f) + (int)(n2 != 0.f) + (int)(n3 != 0.f), L);
-            if (lane == L) {
-                const float nn[3] = {n1, n2, n3};
-                int dst = buf_n;
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    if (nn[q] == 0.f) continue;
-                    float ns = 0.f, ny = 0.f, nx = 0.f, den = 0.f;
-#pragma unroll
-                    for (int d = 0; d < 3; d++) { ns = fmaf(O.sc[q + d], S[q + d], ns); ny += SY[q + d]; nx += SX[q + d]; den += S[q + d]; }
-                    den = __fadd_rn(den, 1e-8f);
-                    cbuf[0][dst] = nn[q];
-                    cbuf[1][dst] = n1;
-                    cbuf[2][dst] = n2;
-                    cbuf[3][dst] = __uint_as_float(((uint32_t)(oi * 3 + q) << SEQ_PIX_BITS) | (uint32_t)(y * w + gx));
-                    cbuf[4][dst] = __fdiv_rn(__fdiv_rn(ns, den), min_size);
-                    cbuf[5][dst] = __fdiv_rn(__fadd_rn(__fdiv_rn(ny, den), (float)y), (float)h);
-                    cbuf[6][dst] = __fdiv_rn(__fadd_rn(__fdiv_rn(nx, den), (float)gx), (float)w);
-                    dst++;
-                }
-            }
-            buf_n += kL;
-        }
-    };
-
-    using I0 = std::integral_constant<int, 0>;
-    using I1 = std::integral_constant<int, 1>;
-    using I2 = std::integral_constant<int, 2>;
 #pragma unroll 1
     for (int c = 0; c < WPD; c++) issue_row(c);
-    // consume pyramid row c: response row j = c-2 (image row r0-3+c) goes to slot j%3; output row y = r0+c-4
+    // consume pyramid row c: response row (image row r0-3+c) enters slot 2; output row y = r0+c-4 sits in slot 1
 #pragma unroll 1
     for (int c = 0; c < n_rows; c++) {
         asm volatile("cp.async.wait_group %0;" ::"n"(WPD - 1) : "memory");
         __syncwarp();
         if (c >= 2) {
-            const int j = c - 2, yy = r0 - 3 + c, y = r0 + c - 4;
-            const int js = j % 3;
-            if (js == 0) { resp_row(c, yy, I0{}); if (c >= 4) nms_row(y, I1{}, I2{}, I0{}); }
-            else if (js == 1) { resp_row(c, yy, I1{}); if (c >= 4) nms_row(y, I2{}, I0{}, I1{}); }
-            else { resp_row(c, yy, I2{}); if (c >= 4) nms_row(y, I0{}, I1{}, I2{}); }
+            const int yy = r0 - 3 + c;
+            const bool in = col_in && yy >= 0 && yy < h;
+            const float (*t)[WROWLEN] = ring[(c - 2) % WRING];
+            const float (*m)[WROWLEN] = ring[(c - 1) % WRING];
+            const float (*bt)[WROWLEN] = ring[c % WRING];
+#pragma unroll
+            for (int d = 0; d < 5; d++) {
+                rs[d][0] = rs[d][1]; rs[d][1] = rs[d][2]; rmx[d][0] = rmx[d][1]; rmx[d][1] = rmx[d][2];
+                hs[d][0] = hs[d][1]; hs[d][1] = hs[d][2]; hx[d][0] = hx[d][1]; hx[d][1] = hx[d][2];
+                float r = 0.f;
+                if (in) r = hessian_regs(t[d][lane], t[d][lane + 1], t[d][lane + 2], m[d][lane], m[d][lane + 1], m[d][lane + 2], bt[d][lane], bt[d][lane + 1],
+                                         bt[d][lane + 2], O.s4[d], P.th);
+                float l = __shfl_up_sync(0xffffffffu, r, 1), rr = __shfl_down_sync(0xffffffffu, r, 1);
+                if (lane == 0) l = 0.f;
+                if (lane == 31) rr = 0.f;
+                rs[d][2] = r;
+                rmx[d][2] = fmaxf(fmaxf(l, r), rr);
+                hs[d][2] = (l + r) + rr;
+                hx[d][2] = fmaf(1.5f, rr, fmaf(0.5f, r, -0.5f * l));   // x offsets [-0.5, 0.5, 1.5] (Q2)
+            }
+        }
+        if (c >= 4) {
+            const int y = r0 + c - 4;
+            float n1 = 0.f, n2 = 0.f, n3 = 0.f;
+            if (col_ok && y >= P.mr_border && y < h - P.mr_border) {
+                float M[5];
+#pragma unroll
+                for (int d = 0; d < 5; d++) M[d] = fmaxf(fmaxf(rmx[d][0], rmx[d][1]), rmx[d][2]);
+                const float x1 = rs[1][1], x2 = rs[2][1], x3 = rs[3][1];
+                n1 = (__fadd_rn(__fsub_rn(x1, fmaxf(fmaxf(M[0], M[1]), M[2])), 1e-5f) > 0.f) ? x1 : 0.f;   // NMS3d, HandCraftedModules.py:220
+                n2 = (__fadd_rn(__fsub_rn(x2, fmaxf(fmaxf(M[1], M[2]), M[3])), 1e-5f) > 0.f) ? x2 : 0.f;
+                n3 = (__fadd_rn(__fsub_rn(x3, fmaxf(fmaxf(M[2], M[3]), M[4])), 1e-5f) > 0.f) ? x3 : 0.f;
+            }
+            const unsigned m1 = __ballot_sync(0xffffffffu, n1 != 0.f), m2 = __ballot_sync(0xffffffffu, n2 != 0.f), m3 = __ballot_sync(0xffffffffu, n3 != 0.f);
+            if (m1 | m2 | m3) {
+                const int row_total = __popc(m1) + __popc(m2) + __popc(m3);
+                if (buf_n + row_total > WCBUF) flush();
+                if ((n1 != 0.f) || (n2 != 0.f) || (n3 != 0.f)) {
+                    var[0] += n1 > 0.f; var[7] += n1 != 0.f;
+#pragma unroll
+                    for (int a1 = 0; a1 < 2; a1++) {
+                        const uint8_t om1 = a1 ? om_after(0, n1) : (uint8_t)0;
+                        const float v2 = masked(n2, om1);
+                        var[1 + a1] += v2 > 0.f; var[8 + a1] += v2 != 0.f;
+#pragma unroll
+                        for (int a2 = 0; a2 < 2; a2++) {
+                            const uint8_t om2 = a2 ? om_after(om1, v2) : om1;
+                            const float v3 = masked(n3, om2);
+                            var[3 + a1 * 2 + a2] += v3 > 0.f; var[10 + a1 * 2 + a2] += v3 != 0.f;
+                        }
+                    }
+                    // soft-argmax (HandCraftedModules.py:266-290) from the rotating horizontal sums: no shuffles, no loop over lanes
+                    const unsigned lt = (1u << lane) - 1u;
+                    const float nn[3] = {n1, n2, n3};
+                    const int pos[3] = {buf_n + __popc(m1 & lt), buf_n + __popc(m1) + __popc(m2 & lt), buf_n + __popc(m1) + __popc(m2) + __popc(m3 & lt)};
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        if (nn[q] == 0.f) continue;
+                        float ns = 0.f, ny = 0.f, nx = 0.f, den = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            const float S = (hs[q + d][0] + hs[q + d][1]) + hs[q + d][2];
+                            ns = fmaf(O.sc[q + d], S, ns);
+                            ny += fmaf(1.5f, hs[q + d][2], fmaf(0.5f, hs[q + d][1], -0.5f * hs[q + d][0]));
+                            nx += (hx[q + d][0] + hx[q + d][1]) + hx[q + d][2];
+                            den += S;
+                        }
+                        den = __fadd_rn(den, 1e-8f);
+                        const int dst = pos[q];
+                        cbuf[0][dst] = nn[q];
+                        cbuf[1][dst] = n1;
+                        cbuf[2][dst] = n2;
+                        cbuf[3][dst] = __uint_as_float(((uint32_t)(oi * 3 + q) << SEQ_PIX_BITS) | (uint32_t)(y * w + gx));
+                        cbuf[4][dst] = __fdiv_rn(__fdiv_rn(ns, den), min_size);
+                        cbuf[5][dst] = __fdiv_rn(__fadd_rn(__fdiv_rn(ny, den), (float)y), (float)h);
+                        cbuf[6][dst] = __fdiv_rn(__fadd_rn(__fdiv_rn(nx, den), (float)gx), (float)w);
+                    }
+                }
+                buf_n += row_total;
+            }
         }
         __syncwarp();            // every lane has finished reading ring rows <= c before slot (c+WPD)%WRING is refilled
         issue_row(c + WPD);
