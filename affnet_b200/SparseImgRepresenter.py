@@ -106,7 +106,8 @@ class ScaleSpaceAffinePatchExtractor(nn.Module):
         seq = self._wrap_i32(ws.d_cand_seq, cap, ws_buf)[:n_cand].to(torch.int64) & 0xFFFFFFFF
         scyx = f32(ws.d_cand_scyx, cap * 3).view(cap, 3)[:n_cand]
         slot = seq >> 27
-        accept = (pos > 1).to(val.device)[slot]
+        live = seq != 0xFFFFFFFF                                    # dropped by the resolve pass
+        accept = live & (pos > 1).to(val.device)[slot.clamp(max=n_slots - 1)]
         order = torch.argsort(torch.where(accept, seq, torch.full_like(seq, 1 << 40)))[:int(accept.sum())]
         val, scyx, slot = val[order], scyx[order], slot[order]
         n_det = self._plan.n_levels - 2

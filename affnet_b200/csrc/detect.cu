@@ -855,7 +855,8 @@ __global__ void __launch_bounds__(SNT) select_kernel(const SelectParams P) {
         P.oct[o] = slot / P.n_det;
         P.lvl[o] = slot % P.n_det;  // detection level_idx - 1: patches come from the level below (:94)
     }
-    if (threadIdx.x == 0) P.count[b] = m_out;
+    // a candidate list that overflowed its capacity is reported as count = -1 (downstream kernels then process no rows)
+    if (threadIdx.x == 0) P.count[b] = (P.cand_count[b] > P.cand_cap) ? -1 : m_out;
 }
 
 }  // namespace ag

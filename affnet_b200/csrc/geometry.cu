@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(GNT) shape_filter_kernel(const ShapeParams P) 
     extern __shared__ unsigned long long s_key[];
     __shared__ int s_surv;
     const int b = blockIdx.x;
-    const int n = min(P.count_in[b], P.cap);
+    const int n = max(0, min(P.count_in[b], P.cap));
     const float* A = P.A + (size_t)b * P.cap * 4;
     const float* L = P.lafs + (size_t)b * P.cap * 6;
     const float* R = P.resp + (size_t)b * P.cap;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(GNT) shape_filter_kernel(const ShapeParams P) 
         P.oct_out[o] = P.oct[(size_t)b * P.cap + i];
         P.lvl_out[o] = P.lvl[(size_t)b * P.cap + i];
     }
-    if (threadIdx.x == 0) P.count_out[b] = m;
+    if (threadIdx.x == 0) P.count_out[b] = (P.count_in[b] < 0) ? -1 : m;   // -1 = upstream capacity overflow, propagated
 }
 
 __global__ void lafs_rotate_kernel(float* __restrict__ lafs, const float* __restrict__ R, int n) {

@@ -33,7 +33,7 @@ int ag_pipeline_create(const ag_pipeline_config_t* cfg, const ag_net_t* affnet, 
     int rc = ag_pyramid_plan(cfg->B, cfg->H, cfg->W, cfg->nlevels, cfg->init_sigma, cfg->border, &p->plan);
     if (rc != AG_OK) { delete p; return rc; }
     p->M = (int)(1.5 * cfg->num_features);  // SparseImgRepresenter.py:194
-    p->cand_cap = cfg->cand_cap > 0 ? cfg->cand_cap : (cfg->H * cfg->W) / 16;
+    p->cand_cap = cfg->cand_cap > 0 ? cfg->cand_cap : (cfg->H * cfg->W) / 8;
     if (p->cand_cap < p->M) p->cand_cap = p->M;
     const size_t B = cfg->B, M = p->M, K = cfg->num_features;
     size_t o = 0;

@@ -48,6 +48,12 @@ class DetectDescribePipeline:
                                         L.ptr(self.desc), L.ptr(self.count), L.stream_ptr()))
         return self.lafs, self.resp, self.desc, self.count
 
+    def check(self):
+        """Synchronises and raises if any image overflowed the candidate capacity (count == -1)."""
+        if bool((self.count < 0).any().item()):
+            raise L.AffnetB200Error("candidate capacity exceeded: construct the pipeline with a larger cand_cap")
+        return self
+
     def capture(self):
         """Capture one run() into a CUDA graph over a static input buffer; use replay(imgs) afterwards."""
         self._static_in = torch.zeros(self.B, 1, self.H, self.W, dtype=torch.float32, device=self.device)

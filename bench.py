@@ -261,6 +261,7 @@ def _main(real_stdout):
 
     sampler = ClockSampler(local) if rank == 0 else None
     total_ms, clocks = timed(step_device, args.steps, args.warmup, sampler)
+    pipe.check()
     n_desc = int(pipe.count.sum().item())
     e2e_ms, _ = timed(step_e2e, args.steps, args.warmup)
 

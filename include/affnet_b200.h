@@ -120,7 +120,8 @@ int ag_detect_level_from_responses(const float* d_low, const float* d_cur, const
  * top num_features by (response desc, seq asc) are returned sorted, otherwise all in
  * (octave, level, raster) order.  num_features <= 0 returns everything (capacity permitting).
  * a_scale multiplies the A part of the LAF (mrSize; SparseImgRepresenter.py:198).
- * Outputs [B, out_cap(,..)]: resp, LAFs (normalised), octave idx, level idx (= detection level-1). */
+ * Outputs [B, out_cap(,..)]: resp, LAFs (normalised), octave idx, level idx (= detection level-1); d_count[b] = -1 if the
+ * candidate list of image b overflowed ws->cand_cap (the caller should retry with a larger capacity). */
 int ag_select_keypoints(const ag_pyramid_plan_t* plan, const ag_detect_ws_t* ws, int num_features, float a_scale,
                         int out_cap, float* d_resp, float* d_lafs, int* d_oct, int* d_lvl, int* d_count,
                         void* stream);
@@ -222,7 +223,7 @@ typedef struct {
     double init_sigma;  /* 1.6 */
     double mrSize;      /* 5.192 */
     int do_ori;         /* 1: OriNet orientation */
-    int cand_cap;       /* candidate capacity per image (0 => H*W/16) */
+    int cand_cap;       /* candidate capacity per image (0 => H*W/8); on overflow the image's count is reported as -1 */
 } ag_pipeline_config_t;
 
 /* Nets are borrowed (must outlive the pipeline).  The pipeline owns no device memory: the caller passes one

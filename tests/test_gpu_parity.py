@@ -341,6 +341,11 @@ def test_full_size_properties(L, nets):
         assert ((desc[b, :n].norm(dim=1) - 1).abs().max() < 1e-4)                         # L2-normalised
         c = lafs[b, :n, :, 2]
         assert bool((c[:, 0] >= 0).all() and (c[:, 0] <= Wd).all() and (c[:, 1] >= 0).all() and (c[:, 1] <= H).all())
+    # candidate overflow is reported, not silently truncated
+    small = DetectDescribePipeline(B, H, Wd, aff, hn, ori, num_features=K, do_ori=True, cand_cap=4000)
+    small.run(imgs)
+    with pytest.raises(Exception):
+        small.check()
     oL, oresp, st = O.detect(imgs[0:1].cpu(), W["affnet"], W["orinet"], K, do_ori=True)
     odesc, _, _ = O.describe(oL, st, W["hardnet"])
     n = int(cnt[0])
