@@ -6,7 +6,9 @@
 
 #include "net_impl.cuh"
 #include "tc_conv.cuh"
+#include "tc_first.cuh"
 #include "tc_head.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace ag {
@@ -44,6 +46,31 @@ static int launch_tc(const __half* in, void* out, const __half* w, const float* 
     kern<<<dim3(gx, NSPLIT), Cfg::THREADS, Cfg::SMEM, st>>>(a, fs);
     AG_CHECK_LAUNCH(FIRST ? "tc_conv_kernel<first>" : "tc_conv_kernel");
     return AG_OK;
+}
+
+template <int C1, int COUT, int SA, int SW, int OSA>
+static int launch_first2(void* out, const __half* w, const float* b, int n, int group, const int* count, cudaStream_t st, const FirstSrc& src) {
+    using Cfg = FirstCfg<C1, COUT, SA, SW, OSA>;
+    auto kern = tc_first2_kernel<C1, COUT, SA, SW, OSA>;
+    static bool configured = false;
+    if (!configured) {
+        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM), "tc_first2 smem attr");
+        if (rc != AG_OK) return rc;
+        configured = true;
+    }
+    ConvArgs a;
+    a.in = nullptr; a.out = out; a.wpk = w; a.bias = b; a.n = n; a.group = group; a.count = count;
+    int gx = num_sms();
+    if (gx > n) gx = n;
+    if (gx < 1) gx = 1;
+    kern<<<gx, 448, Cfg::SMEM, st>>>(a, src);
+    AG_CHECK_LAUNCH("tc_first2_kernel");
+    return AG_OK;
+}
+
+static bool first_simt() {
+    static const bool v = getenv("AG_FIRST_SIMT") != nullptr;   // A/B switch: layer 1 on CUDA cores inside the layer-2 kernel
+    return v;
 }
 
 }  // namespace tc
@@ -86,7 +113,9 @@ int tc_hardnet_forward(const ag_net* net, const tc::FirstSrc& src0, int n, int g
     FirstSrc src = src0;
     src.w1 = net->d_w1; src.b1 = net->d_b[0];
     int rc;
-    if ((rc = launch_tc<32, 32, 32, 1, 1, 2, PHASE, 0, 0, 0, 1>(nullptr, B, net->d_wh[1], net->d_b[1], n, group, count, st, &src))) return rc;
+    if (first_simt()) rc = launch_tc<32, 32, 32, 1, 1, 2, PHASE, 0, 0, 0, 1>(nullptr, B, net->d_wh[1], net->d_b[1], n, group, count, st, &src);
+    else rc = launch_first2<32, 32, 0, 0, 0>(B, net->d_wh[1], net->d_b[1], n, group, count, st, src);
+    if (rc) return rc;
     if ((rc = launch_tc<32, 64, 32, 2, 1, 2, PLAIN>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
     if ((rc = launch_tc<64, 64, 16, 1, 1, 2, PHASE>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
     if ((rc = launch_tc<64, 128, 16, 2, 2, 2, PLAIN>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
@@ -111,7 +140,9 @@ int tc_trunk_affnet(const ag_net* net, const tc::FirstSrc& src0, int n, int grou
     FirstSrc src = src0;
     src.w1 = net->d_w1; src.b1 = net->d_b[0];
     int rc;
-    if ((rc = launch_tc<16, 16, 32, 1, 1, 2, PHASE, 0, 1, 0, 1>(nullptr, B, net->d_wh[1], net->d_b[1], n, group, count, st, &src))) return rc;
+    if (first_simt()) rc = launch_tc<16, 16, 32, 1, 1, 2, PHASE, 0, 1, 0, 1>(nullptr, B, net->d_wh[1], net->d_b[1], n, group, count, st, &src);
+    else rc = launch_first2<16, 16, 0, 1, 0>(B, net->d_wh[1], net->d_b[1], n, group, count, st, src);
+    if (rc) return rc;
     if ((rc = launch_tc<16, 32, 32, 2, 1, 2, PLAIN, 0, 1, 0>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
     if ((rc = launch_tc<32, 32, 16, 1, 1, 2, PHASE, 0, 1, 0>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
     if ((rc = launch_tc<32, 64, 16, 2, 1, 2, PLAIN, 0, 1, 0>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
@@ -129,7 +160,9 @@ int tc_trunk_orinet(const ag_net* net, const tc::FirstSrc& src0, int n, int grou
     FirstSrc src = src0;
     src.w1 = net->d_w1; src.b1 = net->d_b[0];
     int rc;
-    if ((rc = launch_tc<16, 16, 32, 1, 1, 2, PHASE, 1, 1, 1, 1>(nullptr, B, net->d_wh[1], net->d_b[1], n, group, count, st, &src))) return rc;
+    if (first_simt()) rc = launch_tc<16, 16, 32, 1, 1, 2, PHASE, 1, 1, 1, 1>(nullptr, B, net->d_wh[1], net->d_b[1], n, group, count, st, &src);
+    else rc = launch_first2<16, 16, 1, 1, 1>(B, net->d_wh[1], net->d_b[1], n, group, count, st, src);
+    if (rc) return rc;
     if ((rc = launch_tc<16, 32, 32, 2, 1, 2, PLAIN, 1, 1, 1>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
     if ((rc = launch_tc<32, 32, 16, 1, 1, 2, PHASE, 1, 1, 1>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
     if ((rc = launch_tc<32, 64, 16, 2, 1, 2, PLAIN, 1, 1, 1>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;

@@ -1,0 +1,378 @@
+// First two conv layers of AffNet / OriNet / HardNet in ONE kernel, both on tensor cores (sm_100a):
+//
+//   sampler (LAF.py:313-372) -> input_norm (architectures.py:231-235) -> conv3x3(1 -> C1)+BN+ReLU -> conv3x3(C1 -> COUT)+BN+ReLU
+//
+// 32x32 patches and the layer-1 activations never exist in HBM.  Layer 1 (K = 9) is made tensor-core shaped with a sliding
+// window plane: P[slot] = 8 consecutive normalised pixels (fp16), so one 16-byte core-matrix row holds the three horizontal
+// taps (elements 0..2; the weights of elements 3..7 are zero) and the vertical taps are the same plane at +pitch rows: an
+// M=128, K=16 MMA covers two tap rows through the descriptor's leading-byte offset.  Input and weights carry fp16 residual
+// planes (three MMAs per K step), so layer 1 is fp32-grade, as the accuracy budget requires (SURVEY.md §7 hard part 1).
+//
+// Warp roles (448 threads):  0 weight loader | 1 MMA issuer | 2-5 layer-2 epilogue (TMEM -> global, next layout)
+//                            6-9 layer-1 epilogue (TMEM -> bias/ReLU -> fp16 stage in shared memory) | 10-13 sampler + norm + P planes
+#pragma once
+#include "tc_conv.cuh"
+
+namespace ag {
+namespace tc {
+
+template <int C1, int COUT, int SA, int SW, int OSA>
+struct FirstCfg {
+    using In = InLay<32, 1>;     // layout of the stage (input of layer 2)
+    using OutS = InLay<32, 2>;   // layout of the output (input of the stride-2 layer 3)
+    static constexpr int KC = C1 / 8, NT = COUT, TILES = In::TILES;
+    static constexpr int NPIXP = 1280;                         // slots of a P plane: 9*128 rows + 3 pitches of look-ahead, zero tail
+    static constexpr int C1COLS = TILES * C1;                  // TMEM columns of the layer-1 accumulators (one buffer per tile)
+    static constexpr int NACC = ((512 - C1COLS) / NT) < 8 ? ((512 - C1COLS) / NT) : 8;
+    static constexpr uint32_t IN_BYTES = (uint32_t)KC * (1 + SA) * In::NPIX * 16;
+    static constexpr uint32_t W_HALF = 9u * KC * NT * 16, W_BYTES = W_HALF * (1 + SW);
+    static constexpr uint32_t W1_HALF = 4u * C1 * 16, W1_BYTES = 2 * W1_HALF;
+    static constexpr uint32_t P_BYTES = 2u * NPIXP * 16;
+    static constexpr int SX = 1296;                            // floats of one padded fp32 patch buffer (34*34 + zero tail)
+    static constexpr size_t SMEM = 1024 + (size_t)W_BYTES + 2 * (size_t)IN_BYTES + P_BYTES + W1_BYTES + 2 * SX * 4 + 256;
+    static constexpr int OUT_NPIX = OutS::NPIX;
+    static constexpr size_t OUT_BYTES = (size_t)(COUT / 8) * (1 + OSA) * OUT_NPIX * 16;
+    static_assert(C1 % 16 == 0 && NT % 16 == 0 && NT <= 128 && NACC >= 2, "shape");
+    static_assert(SMEM <= 232448, "shared memory budget");
+    static_assert(TILES * 128 + 3 * In::PITCH + 8 <= NPIXP, "P plane look-ahead");
+};
+
+template <int C1, int COUT, int SA, int SW, int OSA>
+__global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, const FirstSrc src) {
+    using Cfg = FirstCfg<C1, COUT, SA, SW, OSA>;
+    using In = typename Cfg::In;
+    constexpr int KC = Cfg::KC, NT = Cfg::NT, NACC = Cfg::NACC, TILES = Cfg::TILES, NPIXP = Cfg::NPIXP, SX = Cfg::SX;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [2]   layer-2 stage filled (128 layer-1 epilogue threads)
+    uint64_t* empty = full + 2;                             // [2]   layer-2 MMAs done with the stage
+    uint64_t* tfull = empty + 2;                            // [8]
+    uint64_t* tempty = tfull + 8;                           // [8]
+    uint64_t* wbar = tempty + 8;
+    uint64_t* p_full = wbar + 1;                            // P planes written (128 producer threads)
+    uint64_t* p_empty = p_full + 1;                         // layer-1 MMAs done with the P planes
+    uint64_t* c1_full = p_empty + 1;                        // [9]
+    uint64_t* c1_empty = c1_full + 9;                       // [9]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c1_empty + 9);
+    float* s_bias1 = reinterpret_cast<float*>(smem + 384);  // [C1]
+    float* s_bias = reinterpret_cast<float*>(smem + 512);   // [NT]
+    unsigned char* sW = smem + 1024;
+    unsigned char* sIn = sW + Cfg::W_BYTES;
+    unsigned char* sP = sIn + 2 * (size_t)Cfg::IN_BYTES;    // [hi|lo][NPIXP][8] fp16
+    unsigned char* sW1 = sP + Cfg::P_BYTES;                 // [hi|lo][4][C1][8] fp16
+    float* s_x = reinterpret_cast<float*>(sW1 + Cfg::W1_BYTES);   // [2][SX]
+    float* s_red = s_x + 2 * SX;                            // [2][4][2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto valid = [&](int pi) -> bool { return a.count == nullptr || (pi % a.group) < a.count[pi / a.group]; };
+    auto next_valid = [&](int pi) -> int {
+        while (pi < a.n && !valid(pi)) pi += gridDim.x;
+        return pi;
+    };
+
+    // ---- one-time setup by all threads: barriers, biases, layer-1 weight operand, zeroed planes / stages ----
+    if (threadIdx.x < NT) s_bias[threadIdx.x] = a.bias[threadIdx.x];
+    if (threadIdx.x < C1) s_bias1[threadIdx.x] = src.b1[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 8; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        mbar_init(wbar, 1); mbar_init(p_full, 128); mbar_init(p_empty, 1);
+        for (int i = 0; i < 9; i++) { mbar_init(&c1_full[i], 1); mbar_init(&c1_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 2 * 4 * C1 * 8; i += blockDim.x) {   // W1[part][chunk dy][cout][e = dx]
+        const int e = i & 7, co = (i >> 3) % C1, dy = (i / (8 * C1)) & 3, part = i / (8 * C1 * 4);
+        float v = 0.f;
+        if (dy < 3 && e < 3) {
+            const float wv = src.w1[(dy * 3 + e) * C1 + co];
+            const __half hi = __float2half_rn(wv);
+            v = part == 0 ? __half2float(hi) : wv - __half2float(hi);
+        }
+        reinterpret_cast<__half*>(sW1)[i] = __float2half_rn(v);
+    }
+    for (int i = threadIdx.x; i < (int)((2 * Cfg::IN_BYTES + Cfg::P_BYTES) / 16); i += blockDim.x) reinterpret_cast<uint4*>(sIn)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 2 * SX; i += blockDim.x) s_x[i] = 0.f;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_l2 = tmem + (uint32_t)Cfg::C1COLS;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(wbar, Cfg::W_BYTES);
+            bulk_g2s(sW, a.wpk, Cfg::W_BYTES, wbar);
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: layer 1 runs one patch ahead of layer 2 =====
+        constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(C1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t leader = elect_one();
+        mbar_wait(wbar, 0);
+        tc_fence_after();
+        const uint32_t w_lo = desc_lo(smem_u32(sW), NT * 16u);
+        const uint32_t w1_lo = desc_lo(smem_u32(sW1), C1 * 16u);
+        const uint32_t p_lo = desc_lo(smem_u32(sP), In::PITCH * 16u);   // leading-byte offset = one tap row
+        auto issue_conv1 = [&](int n1) {
+            mbar_wait(p_full, n1 & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int t = 0; t < TILES; t++) {
+                mbar_wait(&c1_empty[t], (n1 & 1) ^ 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t d = tmem + (uint32_t)(t * C1);
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {   // tap rows (0,1) then (2, zero)
+                        const uint32_t alo = p_lo + (uint32_t)(t * 128 + 2 * j * In::PITCH);
+                        const uint32_t blo = w1_lo + (uint32_t)(2 * j * C1);
+                        if (j == 0) umma_f16_lo<0>(d, alo, blo, idesc1); else umma_f16_lo<1>(d, alo, blo, idesc1);
+                        umma_f16_lo<1>(d, alo + (uint32_t)NPIXP, blo, idesc1);                       // x_lo * w_hi
+                        umma_f16_lo<1>(d, alo, blo + (uint32_t)(Cfg::W1_HALF / 16), idesc1);         // x_hi * w_lo
+                    }
+                    umma_commit(&c1_full[t]);
+                }
+                __syncwarp();
+            }
+            if (leader) umma_commit(p_empty);
+            __syncwarp();
+        };
+        int tcnt = 0;
+        auto issue_l2 = [&](int it) {
+            const int s = it & 1;
+            mbar_wait(&full[s], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t in_lo = desc_lo(smem_u32(sIn + (size_t)s * Cfg::IN_BYTES), In::NPIX * 16u);
+#pragma unroll 1
+            for (int t = 0; t < TILES; t++, tcnt++) {
+                const int ab = tcnt % NACC;
+                mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t d = tmem_l2 + (uint32_t)(ab * NT);
+                    const uint32_t a_t = in_lo + (uint32_t)(t * 128);
+#pragma unroll
+                    for (int tap = 0; tap < 9; tap++) {
+#pragma unroll
+                        for (int j = 0; j < KC / 2; j++) {
+                            const uint32_t alo = a_t + (uint32_t)(In::tap_off(tap / 3, tap % 3) + 2 * j * In::NPIX);
+                            const uint32_t blo = w_lo + (uint32_t)((tap * KC + 2 * j) * NT);
+                            if (tap == 0 && j == 0) umma_f16_lo<0>(d, alo, blo, idesc2); else umma_f16_lo<1>(d, alo, blo, idesc2);
+                            if (SA) umma_f16_lo<1>(d, alo + (uint32_t)(KC * In::NPIX), blo, idesc2);
+                            if (SW) umma_f16_lo<1>(d, alo, blo + (uint32_t)(Cfg::W_HALF / 16), idesc2);
+                        }
+                    }
+                    umma_commit(&tfull[ab]);
+                }
+                __syncwarp();
+            }
+            if (leader) umma_commit(&empty[s]);
+            __syncwarp();
+        };
+        int pi = next_valid(blockIdx.x);
+        if (pi < a.n) issue_conv1(0);
+        int it = 0;
+        while (pi < a.n) {
+            const int pn = next_valid(pi + gridDim.x);
+            if (pn < a.n) issue_conv1(it + 1);
+            issue_l2(it);
+            it++;
+            pi = pn;
+        }
+    } else if (warp < 6) {
+        // ===== layer-2 epilogue: TMEM -> bias + ReLU -> fp16 -> global (layout of the stride-2 consumer) =====
+        const int q = warp & 3, et = (warp - 2) * 32 + lane;
+        int tcnt = 0;
+        for (int pi = next_valid(blockIdx.x); pi < a.n; pi = next_valid(pi + gridDim.x)) {
+            unsigned char* outp = reinterpret_cast<unsigned char*>(a.out) + (size_t)pi * Cfg::OUT_BYTES;
+            constexpr int HB = 33;
+            for (int i = et; i < 4 * HB; i += 128) {   // zero border of the consumer's padded plane
+                const int side = i / HB, k = i - side * HB;
+                int Y, X;
+                if (side == 0) { Y = 0; X = k; } else if (side == 1) { Y = 33; X = k + 1; } else if (side == 2) { Y = k + 1; X = 0; } else { Y = k; X = 33; }
+                const int slot = Cfg::OutS::slot(Y, X);
+#pragma unroll
+                for (int g = 0; g < (NT / 8) * (1 + OSA); g++) *reinterpret_cast<uint4*>(outp + ((size_t)g * Cfg::OUT_NPIX + slot) * 16) = make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll 1
+            for (int t = 0; t < TILES; t++, tcnt++) {
+                const int ab = tcnt % NACC;
+                mbar_wait(&tfull[ab], (tcnt / NACC) & 1);
+                tc_fence_after();
+                const int m = t * 128 + q * 32 + lane;
+                const int y = m / In::PITCH, x = m - y * In::PITCH;
+                const bool ok = (y < 32) && (x < 32);
+                const uint32_t taddr = tmem_l2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NT);
+                uint32_t r[32];
+                if (NT >= 32) {
+                    tmem_ld32(taddr, r);
+                } else {
+                    uint32_t r16[16];
+                    tmem_ld16(taddr, r16);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) { r[i] = r16[i]; r[16 + i] = 0; }
+                }
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[ab]);
+                if (ok) {
+                    const int slot = Cfg::OutS::slot(y + 1, x + 1);
+#pragma unroll
+                    for (int g = 0; g < NT / 8; g++) {
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; e++) v[e] = fmaxf(__uint_as_float(r[g * 8 + e]) + s_bias[g * 8 + e], 0.f);
+                        uint4 pk;
+                        pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
+                        *reinterpret_cast<uint4*>(outp + ((size_t)g * Cfg::OUT_NPIX + slot) * 16) = pk;
+                        if (OSA) {
+                            float l[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e++) l[e] = v[e] - __half2float(__float2half_rn(v[e]));
+                            pk.x = pack_h2(l[0], l[1]); pk.y = pack_h2(l[2], l[3]); pk.z = pack_h2(l[4], l[5]); pk.w = pack_h2(l[6], l[7]);
+                            *reinterpret_cast<uint4*>(outp + ((size_t)(NT / 8 + g) * Cfg::OUT_NPIX + slot) * 16) = pk;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ===== layer-1 epilogue: TMEM -> bias + ReLU -> fp16 (hi [+lo]) -> shared-memory stage of layer 2 =====
+        const int q = warp & 3;
+        int it = 0;
+        for (int pi = next_valid(blockIdx.x); pi < a.n; pi = next_valid(pi + gridDim.x), it++) {
+            const int s = it & 1;
+            mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+            unsigned char* st = sIn + (size_t)s * Cfg::IN_BYTES;
+#pragma unroll 1
+            for (int t = 0; t < TILES; t++) {
+                mbar_wait(&c1_full[t], it & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * C1);
+                uint32_t r[32];
+                if (C1 >= 32) {
+                    tmem_ld32(taddr, r);
+                } else {
+                    uint32_t r16[16];
+                    tmem_ld16(taddr, r16);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) { r[i] = r16[i]; r[16 + i] = 0; }
+                }
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&c1_empty[t]);
+                const int m = t * 128 + q * 32 + lane;
+                const int y = m / In::PITCH, x = m - y * In::PITCH;
+                if (y < 32 && x < 32) {
+                    const int slot = In::slot(y + 1, x + 1);
+#pragma unroll
+                    for (int g = 0; g < C1 / 8; g++) {
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; e++) v[e] = fmaxf(__uint_as_float(r[g * 8 + e]) + s_bias1[g * 8 + e], 0.f);
+                        uint4 pk;
+                        pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
+                        *reinterpret_cast<uint4*>(st + ((size_t)g * In::NPIX + slot) * 16) = pk;
+                        if (SA) {
+                            float l[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e++) l[e] = v[e] - __half2float(__float2half_rn(v[e]));
+                            pk.x = pack_h2(l[0], l[1]); pk.y = pack_h2(l[2], l[3]); pk.z = pack_h2(l[4], l[5]); pk.w = pack_h2(l[6], l[7]);
+                            *reinterpret_cast<uint4*>(st + ((size_t)(KC + g) * In::NPIX + slot) * 16) = pk;
+                        }
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&full[s]);
+        }
+    } else {
+        // ===== producers: sampler (or patch load) -> input_norm -> sliding-window planes P_hi / P_lo =====
+        const int pt = threadIdx.x - 320;   // 0..127
+        const int pw = warp - 10;
+        float tp[8][4], fx[8], fy[8];
+        auto issue_fetch = [&](int pi) {
+            if (src.patches != nullptr) {
+                const float* pp = src.patches + (size_t)pi * 1024;
+#pragma unroll
+                for (int k = 0; k < 8; k++) { tp[k][0] = pp[pt + k * 128]; tp[k][1] = tp[k][2] = tp[k][3] = 0.f; fx[k] = 0.f; fy[k] = 0.f; }
+            } else {
+                const int b = pi / src.cap;
+                const int o = min(max(src.oct[pi], 0), src.geom.n_octaves - 1), l = min(max(src.lvl[pi], 0), src.geom.n_levels - 1);
+                const int h = src.geom.h[o], w = src.geom.w[o];
+                const float* img = src.pyr + src.geom.off[o][l] + (size_t)b * h * w;
+                const float* Lf = src.lafs + (size_t)pi * 6;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int p = pt + k * 128;
+                    float px, py;
+                    laf_sample_xy(Lf, h, w, p >> 5, p & 31, 1.0f / 32.0f, px, py);
+                    bilinear_taps(img, h, w, px, py, tp[k], fx[k], fy[k]);
+                }
+            }
+        };
+        int pi = next_valid(blockIdx.x);
+        if (pi < a.n) issue_fetch(pi);
+        int it = 0;
+        while (pi < a.n) {
+            float* sx = s_x + (it & 1) * SX;
+            float* red = s_red + (it & 1) * 8;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = bilinear_combine(tp[k], fx[k], fy[k]);
+            const int pn = next_valid(pi + gridDim.x);
+            if (pn < a.n) issue_fetch(pn);
+            // input_norm: mean, unbiased std + 1e-7 (two passes, as the reference)
+            float sm = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+            for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+            if (lane == 0) red[pw * 2] = sm;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const float mean = ((red[0] + red[2]) + (red[4] + red[6])) / 1024.f;
+            float qs = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const float d = v[k] - mean; qs = fmaf(d, d, qs); }
+            for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
+            if (lane == 0) red[pw * 2 + 1] = qs;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const float inv = 1.f / (sqrtf(((red[1] + red[3]) + (red[5] + red[7])) / 1023.f) + 1e-7f);
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const int p = pt + k * 128; sx[((p >> 5) + 1) * 34 + (p & 31) + 1] = (v[k] - mean) * inv; }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(p_empty, (it & 1) ^ 1);   // layer-1 MMAs of the previous patch have consumed the planes
+#pragma unroll 1
+            for (int k = 0; k < NPIXP / 128; k++) {
+                const int s0 = pt + k * 128;
+                float xv[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) xv[e] = sx[s0 + e];
+                uint4 hi, lo;
+                float r8[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) r8[e] = xv[e] - __half2float(__float2half_rn(xv[e]));
+                hi.x = pack_h2(xv[0], xv[1]); hi.y = pack_h2(xv[2], xv[3]); hi.z = pack_h2(xv[4], xv[5]); hi.w = pack_h2(xv[6], xv[7]);
+                lo.x = pack_h2(r8[0], r8[1]); lo.y = pack_h2(r8[2], r8[3]); lo.z = pack_h2(r8[4], r8[5]); lo.w = pack_h2(r8[6], r8[7]);
+                *reinterpret_cast<uint4*>(sP + (size_t)s0 * 16) = hi;
+                *reinterpret_cast<uint4*>(sP + (size_t)(NPIXP + s0) * 16) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(p_full);
+            it++;
+            pi = pn;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
+}  // namespace tc
+}  // namespace ag
