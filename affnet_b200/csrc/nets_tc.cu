@@ -143,10 +143,10 @@ int tc_trunk_affnet(const ag_net* net, const tc::FirstSrc& src0, int n, int grou
     if (first_simt()) rc = launch_tc<16, 16, 32, 1, 1, 2, PHASE, 0, 1, 0, 1>(nullptr, B, net->d_wh[1], net->d_b[1], n, group, count, st, &src);
     else rc = launch_first2<16, 16, 0, 1, 0>(B, net->d_wh[1], net->d_b[1], n, group, count, st, src);
     if (rc) return rc;
-    if ((rc = launch_tc<16, 32, 32, 2, 1, 2, PLAIN, 0, 1, 0>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
-    if ((rc = launch_tc<32, 32, 16, 1, 1, 2, PHASE, 0, 1, 0>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
-    if ((rc = launch_tc<32, 64, 16, 2, 1, 2, PLAIN, 0, 1, 0>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
-    if ((rc = launch_tc<64, 64, 8, 1, 1, 2, FINAL, 0, 1, 0>(A, feat, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
+    if ((rc = launch_tc<16, 32, 32, 2, 1, 4, PLAIN, 0, 1, 0>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
+    if ((rc = launch_tc<32, 32, 16, 1, 1, 6, PHASE, 0, 1, 0>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
+    if ((rc = launch_tc<32, 64, 16, 2, 1, 5, PLAIN, 0, 1, 0>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
+    if ((rc = launch_tc<64, 64, 8, 1, 1, 4, FINAL, 0, 1, 0>(A, feat, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
     return AG_OK;
 }
 
@@ -164,7 +164,7 @@ int tc_trunk_orinet(const ag_net* net, const tc::FirstSrc& src0, int n, int grou
     else rc = launch_first2<16, 16, 1, 1, 1>(B, net->d_wh[1], net->d_b[1], n, group, count, st, src);
     if (rc) return rc;
     if ((rc = launch_tc<16, 32, 32, 2, 1, 2, PLAIN, 1, 1, 1>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
-    if ((rc = launch_tc<32, 32, 16, 1, 1, 2, PHASE, 1, 1, 1>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
+    if ((rc = launch_tc<32, 32, 16, 1, 1, 3, PHASE, 1, 1, 1>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
     if ((rc = launch_tc<32, 64, 16, 2, 1, 2, PLAIN, 1, 1, 1>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
     if ((rc = launch_tc<64, 64, 8, 1, 1, 2, FINAL, 1, 1, 0>(A, feat, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
     return AG_OK;

@@ -225,8 +225,11 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
 #pragma unroll
                     for (int g = 0; g < NT / 8; g++) {
                         float v[8];
-#pragma unroll
-                        for (int e = 0; e < 8; e++) v[e] = fmaxf(__uint_as_float(r[g * 8 + e]) + s_bias[g * 8 + e], 0.f);
+                        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + g * 8), b1 = *reinterpret_cast<const float4*>(s_bias + g * 8 + 4);
+                        v[0] = fmaxf(__uint_as_float(r[g * 8 + 0]) + b0.x, 0.f); v[1] = fmaxf(__uint_as_float(r[g * 8 + 1]) + b0.y, 0.f);
+                        v[2] = fmaxf(__uint_as_float(r[g * 8 + 2]) + b0.z, 0.f); v[3] = fmaxf(__uint_as_float(r[g * 8 + 3]) + b0.w, 0.f);
+                        v[4] = fmaxf(__uint_as_float(r[g * 8 + 4]) + b1.x, 0.f); v[5] = fmaxf(__uint_as_float(r[g * 8 + 5]) + b1.y, 0.f);
+                        v[6] = fmaxf(__uint_as_float(r[g * 8 + 6]) + b1.z, 0.f); v[7] = fmaxf(__uint_as_float(r[g * 8 + 7]) + b1.w, 0.f);
                         uint4 pk;
                         pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
                         *reinterpret_cast<uint4*>(outp + ((size_t)g * Cfg::OUT_NPIX + slot) * 16) = pk;
@@ -274,8 +277,11 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
 #pragma unroll
                     for (int g = 0; g < C1 / 8; g++) {
                         float v[8];
-#pragma unroll
-                        for (int e = 0; e < 8; e++) v[e] = fmaxf(__uint_as_float(r[g * 8 + e]) + s_bias1[g * 8 + e], 0.f);
+                        const float4 b0 = *reinterpret_cast<const float4*>(s_bias1 + g * 8), b1 = *reinterpret_cast<const float4*>(s_bias1 + g * 8 + 4);
+                        v[0] = fmaxf(__uint_as_float(r[g * 8 + 0]) + b0.x, 0.f); v[1] = fmaxf(__uint_as_float(r[g * 8 + 1]) + b0.y, 0.f);
+                        v[2] = fmaxf(__uint_as_float(r[g * 8 + 2]) + b0.z, 0.f); v[3] = fmaxf(__uint_as_float(r[g * 8 + 3]) + b0.w, 0.f);
+                        v[4] = fmaxf(__uint_as_float(r[g * 8 + 4]) + b1.x, 0.f); v[5] = fmaxf(__uint_as_float(r[g * 8 + 5]) + b1.y, 0.f);
+                        v[6] = fmaxf(__uint_as_float(r[g * 8 + 6]) + b1.z, 0.f); v[7] = fmaxf(__uint_as_float(r[g * 8 + 7]) + b1.w, 0.f);
                         uint4 pk;
                         pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
                         *reinterpret_cast<uint4*>(st + ((size_t)g * In::NPIX + slot) * 16) = pk;
@@ -297,11 +303,13 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
         const int pt = threadIdx.x - 320;   // 0..127
         const int pw = warp - 10;
         float tp[8][4], fx[8], fy[8];
+        // pixel k of this thread: warp pw owns patch block-rows {2pw, 2pw+1} (4 rows each); k = block (4 rows x 8 cols), lane = cell
+        auto pix_of = [&](int k) -> int { return ((pw * 2 + (k >> 2)) * 4 + (lane >> 3)) * 32 + (k & 3) * 8 + (lane & 7); };
         auto issue_fetch = [&](int pi) {
             if (src.patches != nullptr) {
                 const float* pp = src.patches + (size_t)pi * 1024;
 #pragma unroll
-                for (int k = 0; k < 8; k++) { tp[k][0] = pp[pt + k * 128]; tp[k][1] = tp[k][2] = tp[k][3] = 0.f; fx[k] = 0.f; fy[k] = 0.f; }
+                for (int k = 0; k < 8; k++) { tp[k][0] = pp[pix_of(k)]; tp[k][1] = tp[k][2] = tp[k][3] = 0.f; fx[k] = 0.f; fy[k] = 0.f; }
             } else {
                 const int b = pi / src.cap;
                 const int o = min(max(src.oct[pi], 0), src.geom.n_octaves - 1), l = min(max(src.lvl[pi], 0), src.geom.n_levels - 1);
@@ -310,7 +318,7 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
                 const float* Lf = src.lafs + (size_t)pi * 6;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const int p = pt + k * 128;
+                    const int p = pix_of(k);
                     float px, py;
                     laf_sample_xy(Lf, h, w, p >> 5, p & 31, 1.0f / 32.0f, px, py);
                     bilinear_taps(img, h, w, px, py, tp[k], fx[k], fy[k]);
@@ -342,7 +350,7 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const float inv = 1.f / (sqrtf(((red[1] + red[3]) + (red[5] + red[7])) / 1023.f) + 1e-7f);
 #pragma unroll
-            for (int k = 0; k < 8; k++) { const int p = pt + k * 128; sx[((p >> 5) + 1) * 34 + (p & 31) + 1] = (v[k] - mean) * inv; }
+            for (int k = 0; k < 8; k++) { const int p = pix_of(k); sx[((p >> 5) + 1) * 34 + (p & 31) + 1] = (v[k] - mean) * inv; }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(p_empty, (it & 1) ^ 1);   // layer-1 MMAs of the previous patch have consumed the planes
 #pragma unroll 1
