@@ -340,7 +340,7 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
         packed.insert(packed.end(), bias, bias + no);
         while (packed.size() % 4) packed.push_back(0.f);
     }
-    // fp16 packs for the tensor-core engine: [nsplit][hi|lo][9][cin/8][cout/nsplit][8], layers 1..5
+    // fp16 packs for the tensor-core engine: [nsplit][9][cin/8][hi rows | lo rows][8], layers 1..5
     std::vector<__half> packed_h;
     size_t wh_off[6] = {0, 0, 0, 0, 0, 0};
     const int sw = tc_split_w(kind);
@@ -351,15 +351,16 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
         packed_h.resize(packed_h.size() + (size_t)9 * ci * co * (1 + sw));
         __half* dst = packed_h.data() + wh_off[l];
         for (int sp = 0; sp < ns; sp++)
-            for (int part = 0; part <= sw; part++)
-                for (int tap = 0; tap < 9; tap++)
-                    for (int g = 0; g < kc; g++)
+            for (int tap = 0; tap < 9; tap++)
+                for (int g = 0; g < kc; g++)
+                    for (int part = 0; part <= sw; part++)
                         for (int nn = 0; nn < nt; nn++)
                             for (int e = 0; e < 8; e++) {
                                 const float v = wf[((size_t)tap * ci + g * 8 + e) * co + sp * nt + nn];
                                 const __half hi = __float2half_rn(v);
                                 const __half val = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
-                                dst[(((((size_t)sp * (1 + sw) + part) * 9 + tap) * kc + g) * nt + nn) * 8 + e] = val;
+                                // [nsplit][9][kc][hi rows | lo rows][8]
+                                dst[(((((size_t)sp * 9 + tap) * kc + g) * (1 + sw) + part) * nt + nn) * 8 + e] = val;
                             }
     }
     size_t headh_off = 0;

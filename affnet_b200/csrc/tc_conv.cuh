@@ -143,7 +143,7 @@ struct FirstSrc {
 struct ConvArgs {
     const __half* in;     // [n][CIN/8][NPIX_IN][8]
     void* out;            // next layer's canonical fp16 buffer, or fp32 [n][COUT][HOUT][HOUT]
-    const __half* wpk;    // [NSPLIT][hi|lo][9][CIN/8][COUT/NSPLIT][8]  (lo block only if SW)
+    const __half* wpk;    // [NSPLIT][9][CIN/8][hi rows | lo rows][8]: (1+SW)*COUT/NSPLIT rows per K chunk
     const float* bias;    // [COUT]
     int n, group;
     const int* count;
@@ -160,8 +160,12 @@ struct ConvCfg {
     static constexpr int HOUT = H / STRIDE;
     static constexpr int KC = CIN / 8;                  // 16-byte channel groups
     static constexpr int NT = COUT / NSPLIT;            // MMA N
-    static constexpr int NACC = (512 / NT) < 8 ? (512 / NT) : 8;   // TMEM accumulator buffers: the issuer runs up to NACC tiles ahead
-    static constexpr int TMEM_COLS = (NACC * NT <= 32) ? 32 : (NACC * NT <= 64) ? 64 : (NACC * NT <= 128) ? 128 : (NACC * NT <= 256) ? 256 : 512;
+    // With split weights the B operand stacks W_hi and W_lo along N (rows [0,NT) hi, [NT,2NT) lo of every K chunk): ONE MMA of
+    // N = 2*NT yields A*W_hi and A*W_lo side by side in TMEM and the epilogue adds the two halves.  The MMA is bound by the
+    // shared-memory read of its A operand (4 KB per 128x16 tile), so halving the MMA count halves the time.
+    static constexpr int ACCW = NT * (1 + SW);                      // accumulator width in TMEM columns
+    static constexpr int NACC = (512 / ACCW) < 8 ? (512 / ACCW) : 8;  // accumulator buffers: the issuer runs up to NACC tiles ahead
+    static constexpr int TMEM_COLS = (NACC * ACCW <= 32) ? 32 : (NACC * ACCW <= 64) ? 64 : (NACC * ACCW <= 128) ? 128 : (NACC * ACCW <= 256) ? 256 : 512;
     static constexpr uint32_t IN_BYTES = (uint32_t)KC * (1 + SA) * In::NPIX * 16;     // one patch
     static constexpr uint32_t W_HALF = 9u * KC * NT * 16;
     static constexpr uint32_t W_BYTES = W_HALF * (1 + SW);
@@ -175,7 +179,7 @@ struct ConvCfg {
     static constexpr size_t OUT_BYTES = (OUT == FINAL) ? (size_t)COUT * HOUT * HOUT * 4
                                         : (OUT == HEADL) ? (size_t)COUT * HOUT * HOUT * 2
                                                          : (size_t)(COUT / 8) * (1 + OSA) * OUT_NPIX * 16;
-    static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT <= 128, "UMMA shape / bias staging");
+    static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT <= 128 && ACCW <= 256, "UMMA shape / bias staging");
     static_assert(2 * STAGES + 2 * NACC + 1 <= 60, "barrier area");
     static_assert(SMEM <= 232448, "shared memory budget");
 };
@@ -235,11 +239,12 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues =====
-        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(Cfg::ACCW >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N = NT or 2*NT
+        constexpr uint32_t idesc_hi = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);       // N = NT (hi rows only)
         const uint32_t leader = elect_one();
         mbar_wait(wbar, 0);
         tc_fence_after();
-        const uint32_t w_lo = desc_lo(smem_u32(sW), NT * 16u);
+        const uint32_t w_lo = desc_lo(smem_u32(sW), Cfg::ACCW * 16u);
         int it = 0, tcnt = 0;
         for (int pi = blockIdx.x; pi < a.n; pi += gridDim.x) {
             if (!valid(pi)) continue;
@@ -253,18 +258,17 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
                 mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1);
                 tc_fence_after();
                 if (leader) {
-                    const uint32_t d_tmem = tmem + (uint32_t)(ab * NT);
+                    const uint32_t d_tmem = tmem + (uint32_t)(ab * Cfg::ACCW);
                     const uint32_t a_t = in_lo + (uint32_t)(t * 128);  // 16-byte units
 #pragma unroll
                     for (int tap = 0; tap < 9; tap++) {
 #pragma unroll
                         for (int j = 0; j < KC / 2; j++) {
                             const uint32_t alo = a_t + (uint32_t)(In::tap_off(tap / 3, tap % 3) + 2 * j * In::NPIX);
-                            const uint32_t blo = w_lo + (uint32_t)((tap * KC + 2 * j) * NT);
-                            if (tap == 0 && j == 0) umma_f16_lo<0>(d_tmem, alo, blo, idesc);
+                            const uint32_t blo = w_lo + (uint32_t)((tap * KC + 2 * j) * Cfg::ACCW);
+                            if (tap == 0 && j == 0) umma_f16_lo<0>(d_tmem, alo, blo, idesc);                      // A_hi * [W_hi ; W_lo]
                             else umma_f16_lo<1>(d_tmem, alo, blo, idesc);
-                            if (SA) umma_f16_lo<1>(d_tmem, alo + (uint32_t)(KC * In::NPIX), blo, idesc);          // A_lo * W_hi
-                            if (SW) umma_f16_lo<1>(d_tmem, alo, blo + (uint32_t)(Cfg::W_HALF / 16), idesc);       // A_hi * W_lo
+                            if (SA) umma_f16_lo<1>(d_tmem, alo + (uint32_t)(KC * In::NPIX), blo, idesc_hi);       // A_lo * W_hi -> hi columns
                         }
                     }
                     umma_commit(&tfull[ab]);
@@ -428,17 +432,30 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
                 const int m = t * 128 + q * 32 + lane;
                 const int y = m / In::PITCH, x = m - y * In::PITCH;
                 const bool ok = (y < HOUT) && (x < HOUT);
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NT);
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACCW);
 #pragma unroll
                 for (int c0 = 0; c0 < NT; c0 += 32) {
                     uint32_t r[32];
                     if (NT - c0 >= 32) {
                         tmem_ld32(taddr + c0, r);
+                        if (SW) {   // add the A*W_lo half
+                            uint32_t r2[32];
+                            tmem_ld32(taddr + NT + c0, r2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+                        }
                     } else {
                         uint32_t r16[16];
                         tmem_ld16(taddr + c0, r16);
 #pragma unroll
                         for (int i = 0; i < 16; i++) { r[i] = r16[i]; r[16 + i] = 0; }
+                        if (SW) {
+                            tmem_ld16(taddr + NT + c0, r16);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r16[i]));
+                        }
                     }
                     tmem_ld_wait();
                     if (c0 + 32 >= NT) {  // last column chunk read: release the accumulator buffer

@@ -22,8 +22,12 @@ struct FirstCfg {
     using OutS = InLay<32, 2>;   // layout of the output (input of the stride-2 layer 3)
     static constexpr int KC = C1 / 8, NT = COUT, TILES = In::TILES;
     static constexpr int NPIXP = 1280;                         // slots of a P plane: 9*128 rows + 3 pitches of look-ahead, zero tail
-    static constexpr int C1COLS = TILES * C1;                  // TMEM columns of the layer-1 accumulators (one buffer per tile)
-    static constexpr int NACC = ((512 - C1COLS) / NT) < 8 ? ((512 - C1COLS) / NT) : 8;
+    // stacked-N operands (see ConvCfg::ACCW): layer 2 when SW; layer 1 when its nine accumulators still fit TMEM (C1 = 16)
+    static constexpr int S1 = (TILES * 2 * C1 + 2 * NT * (1 + SW) <= 512) ? 1 : 0;
+    static constexpr int ACC1 = C1 * (1 + S1);                 // layer-1 accumulator width
+    static constexpr int ACCW = NT * (1 + SW);                 // layer-2 accumulator width
+    static constexpr int C1COLS = TILES * ACC1;                // TMEM columns of the layer-1 accumulators (one buffer per tile)
+    static constexpr int NACC = ((512 - C1COLS) / ACCW) < 8 ? ((512 - C1COLS) / ACCW) : 8;
     static constexpr uint32_t IN_BYTES = (uint32_t)KC * (1 + SA) * In::NPIX * 16;
     static constexpr uint32_t W_HALF = 9u * KC * NT * 16, W_BYTES = W_HALF * (1 + SW);
     static constexpr uint32_t W1_HALF = 4u * C1 * 16, W1_BYTES = 2 * W1_HALF;
@@ -32,7 +36,7 @@ struct FirstCfg {
     static constexpr size_t SMEM = 1024 + (size_t)W_BYTES + 2 * (size_t)IN_BYTES + P_BYTES + W1_BYTES + 2 * SX * 4 + 256;
     static constexpr int OUT_NPIX = OutS::NPIX;
     static constexpr size_t OUT_BYTES = (size_t)(COUT / 8) * (1 + OSA) * OUT_NPIX * 16;
-    static_assert(C1 % 16 == 0 && NT % 16 == 0 && NT <= 128 && NACC >= 2, "shape");
+    static_assert(C1 % 16 == 0 && NT % 16 == 0 && NT <= 128 && NACC >= 2 && ACCW <= 256, "shape");
     static_assert(SMEM <= 232448, "shared memory budget");
     static_assert(TILES * 128 + 3 * In::PITCH + 8 <= NPIXP, "P plane look-ahead");
 };
@@ -79,8 +83,8 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
         for (int i = 0; i < 9; i++) { mbar_init(&c1_full[i], 1); mbar_init(&c1_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 2 * 4 * C1 * 8; i += blockDim.x) {   // W1[part][chunk dy][cout][e = dx]
-        const int e = i & 7, co = (i >> 3) % C1, dy = (i / (8 * C1)) & 3, part = i / (8 * C1 * 4);
+    for (int i = threadIdx.x; i < 2 * 4 * C1 * 8; i += blockDim.x) {   // W1[chunk dy][hi rows | lo rows][e = dx]
+        const int e = i & 7, co = (i >> 3) % C1, part = (i / (8 * C1)) & 1, dy = i / (8 * C1 * 2);
         float v = 0.f;
         if (dy < 3 && e < 3) {
             const float wv = src.w1[(dy * 3 + e) * C1 + co];
@@ -109,13 +113,15 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
         }
     } else if (warp == 1) {
         // ===== MMA issuer: layer 1 runs one patch ahead of layer 2 =====
-        constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)(Cfg::ACCW >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc2_hi = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(C1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc1_st = (1u << 4) | ((uint32_t)((2 * C1) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t leader = elect_one();
         mbar_wait(wbar, 0);
         tc_fence_after();
-        const uint32_t w_lo = desc_lo(smem_u32(sW), NT * 16u);
-        const uint32_t w1_lo = desc_lo(smem_u32(sW1), C1 * 16u);
+        const uint32_t w_lo = desc_lo(smem_u32(sW), Cfg::ACCW * 16u);
+        const uint32_t w1_lo = desc_lo(smem_u32(sW1), 2 * C1 * 16u);   // K chunks are 2*C1 rows apart (hi rows, then lo rows)
         const uint32_t p_lo = desc_lo(smem_u32(sP), In::PITCH * 16u);   // leading-byte offset = one tap row
         auto issue_conv1 = [&](int n1) {
             mbar_wait(p_full, n1 & 1);
@@ -125,14 +131,19 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
                 mbar_wait(&c1_empty[t], (n1 & 1) ^ 1);
                 tc_fence_after();
                 if (leader) {
-                    const uint32_t d = tmem + (uint32_t)(t * C1);
+                    const uint32_t d = tmem + (uint32_t)(t * Cfg::ACC1);
 #pragma unroll
                     for (int j = 0; j < 2; j++) {   // tap rows (0,1) then (2, zero)
                         const uint32_t alo = p_lo + (uint32_t)(t * 128 + 2 * j * In::PITCH);
-                        const uint32_t blo = w1_lo + (uint32_t)(2 * j * C1);
-                        if (j == 0) umma_f16_lo<0>(d, alo, blo, idesc1); else umma_f16_lo<1>(d, alo, blo, idesc1);
-                        umma_f16_lo<1>(d, alo + (uint32_t)NPIXP, blo, idesc1);                       // x_lo * w_hi
-                        umma_f16_lo<1>(d, alo, blo + (uint32_t)(Cfg::W1_HALF / 16), idesc1);         // x_hi * w_lo
+                        const uint32_t blo = w1_lo + (uint32_t)(2 * j * 2 * C1);
+                        if (Cfg::S1) {   // x_hi * [w_hi ; w_lo] in one MMA, then x_lo * w_hi
+                            if (j == 0) umma_f16_lo<0>(d, alo, blo, idesc1_st); else umma_f16_lo<1>(d, alo, blo, idesc1_st);
+                            umma_f16_lo<1>(d, alo + (uint32_t)NPIXP, blo, idesc1);
+                        } else {
+                            if (j == 0) umma_f16_lo<0>(d, alo, blo, idesc1); else umma_f16_lo<1>(d, alo, blo, idesc1);
+                            umma_f16_lo<1>(d, alo + (uint32_t)NPIXP, blo, idesc1);               // x_lo * w_hi
+                            umma_f16_lo<1>(d, alo, blo + (uint32_t)C1, idesc1);                   // x_hi * w_lo (lo rows follow the hi rows)
+                        }
                     }
                     umma_commit(&c1_full[t]);
                 }
@@ -153,17 +164,16 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
                 mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1);
                 tc_fence_after();
                 if (leader) {
-                    const uint32_t d = tmem_l2 + (uint32_t)(ab * NT);
+                    const uint32_t d = tmem_l2 + (uint32_t)(ab * Cfg::ACCW);
                     const uint32_t a_t = in_lo + (uint32_t)(t * 128);
 #pragma unroll
                     for (int tap = 0; tap < 9; tap++) {
 #pragma unroll
                         for (int j = 0; j < KC / 2; j++) {
                             const uint32_t alo = a_t + (uint32_t)(In::tap_off(tap / 3, tap % 3) + 2 * j * In::NPIX);
-                            const uint32_t blo = w_lo + (uint32_t)((tap * KC + 2 * j) * NT);
+                            const uint32_t blo = w_lo + (uint32_t)((tap * KC + 2 * j) * Cfg::ACCW);
                             if (tap == 0 && j == 0) umma_f16_lo<0>(d, alo, blo, idesc2); else umma_f16_lo<1>(d, alo, blo, idesc2);
-                            if (SA) umma_f16_lo<1>(d, alo + (uint32_t)(KC * In::NPIX), blo, idesc2);
-                            if (SW) umma_f16_lo<1>(d, alo, blo + (uint32_t)(Cfg::W_HALF / 16), idesc2);
+                            if (SA) umma_f16_lo<1>(d, alo + (uint32_t)(KC * In::NPIX), blo, idesc2_hi);
                         }
                     }
                     umma_commit(&tfull[ab]);
@@ -206,15 +216,28 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
                 const int m = t * 128 + q * 32 + lane;
                 const int y = m / In::PITCH, x = m - y * In::PITCH;
                 const bool ok = (y < 32) && (x < 32);
-                const uint32_t taddr = tmem_l2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NT);
+                const uint32_t taddr = tmem_l2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACCW);
                 uint32_t r[32];
                 if (NT >= 32) {
                     tmem_ld32(taddr, r);
+                    if (SW) {
+                        uint32_t r2[32];
+                        tmem_ld32(taddr + NT, r2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+                    }
                 } else {
                     uint32_t r16[16];
                     tmem_ld16(taddr, r16);
 #pragma unroll
                     for (int i = 0; i < 16; i++) { r[i] = r16[i]; r[16 + i] = 0; }
+                    if (SW) {
+                        tmem_ld16(taddr + NT, r16);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r16[i]));
+                    }
                 }
                 tmem_ld_wait();
                 tc_fence_before();
@@ -256,10 +279,15 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
             for (int t = 0; t < TILES; t++) {
                 mbar_wait(&c1_full[t], it & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * C1);
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * Cfg::ACC1);
                 uint32_t r[32];
                 if (C1 >= 32) {
                     tmem_ld32(taddr, r);
+                } else if (Cfg::S1) {   // [x*w_hi | x_hi*w_lo] side by side: one 32-column load, add the halves
+                    tmem_ld32(taddr, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r[16 + i]));
                 } else {
                     uint32_t r16[16];
                     tmem_ld16(taddr, r16);
