@@ -16,7 +16,7 @@ struct ag_net {
     float* d_w1;       // == d_w[0]
     __half* d_wh[6];   // fp16 [nsplit][hi|lo][9][cin/8][cout/nsplit][8] for layers 1..5 (index 0 unused; lo only for AffNet/OriNet)
     __half* d_headh;   // HardNet head for the tensor-core GEMM: fp16 [8192/8][128][8], k = (pixel*16 + c/8)*8 + c%8
-    float* d_head_w;   // AffNet [3][4096], OriNet [2][4096], HardNet [8192][128]
+    float* d_head_w;   // AffNet [3][4096], OriNet w_eff[4096][18] (per-position shifted copies), HardNet [8192][128]
     float* d_head_b;   // AffNet bias[3], OriNet bias[2], HardNet {scale[128], shift[128]}
     float* d_all;      // fp32 allocation
     __half* d_all_h;   // fp16 allocation

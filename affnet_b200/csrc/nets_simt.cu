@@ -175,50 +175,62 @@ __global__ void affnet_head_kernel(const float* __restrict__ feat, const float* 
     }
 }
 
-// OriNet: conv8x8(64->2, padding=1)+bias on the 8x8 map -> 3x3, tanh, mean, atan2, rotation (architectures.py:57-59,76-82)
-__global__ void orinet_head_kernel(const float* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
-                                   float* __restrict__ out, float* __restrict__ angle_out, int n, int group,
-                                   const int* __restrict__ count) {
-    const int pi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (pi >= n) return;
-    if (count != nullptr && (pi % group) >= count[pi / group]) return;
-    const float* f = feat + (size_t)pi * 4096;
-    float acc[2][9];
+// OriNet: conv8x8(64->2, padding=1)+bias on the 8x8 map -> 3x3, tanh, mean, atan2, rotation (architectures.py:57-59,76-82).
+// The padded 8x8 kernel sliding over an 8x8 map is 18 dot products of length 4096 against per-position shifted copies of the
+// weights (w_eff[k][c*9 + oy*3 + ox], built at upload): one warp handles 4 patches, lanes stride over k, the 72 accumulators
+// are reduced by shuffles; weights go through shared memory in chunks so every CTA reads them once.
+constexpr int OH_P = 4, OH_W = 8, OH_KC = 256;   // patches per warp, warps per CTA, k-chunk
+__global__ void __launch_bounds__(OH_W * 32) orinet_head_kernel(const float* __restrict__ feat, const float* __restrict__ weff, const float* __restrict__ bias,
+                                                                 float* __restrict__ out, float* __restrict__ angle_out, int n, int group,
+                                                                 const int* __restrict__ count) {
+    __shared__ __align__(16) float s_w[OH_KC][20];   // 18 used, rows padded to 80 B
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p0 = (blockIdx.x * OH_W + warp) * OH_P;
+    float acc[OH_P][18];
 #pragma unroll
-    for (int c = 0; c < 2; c++)
+    for (int q = 0; q < OH_P; q++)
 #pragma unroll
-        for (int q = 0; q < 9; q++) acc[c][q] = 0.f;
-    for (int i = lane; i < 4096; i += 32) {
-        const int ci = i >> 6, ky = (i >> 3) & 7, kx = i & 7;
-        const float w0 = __ldg(w + i), w1 = __ldg(w + 4096 + i);
+        for (int o = 0; o < 18; o++) acc[q][o] = 0.f;
+    const float* f[OH_P];
 #pragma unroll
-        for (int oy = 0; oy < 3; oy++) {
-            const int iy = oy + ky - 1;
-            if (iy < 0 || iy > 7) continue;
+    for (int q = 0; q < OH_P; q++) f[q] = feat + (size_t)min(p0 + q, n - 1) * 4096;
+    for (int k0 = 0; k0 < 4096; k0 += OH_KC) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < OH_KC * 18; i += OH_W * 32) s_w[i / 18][i % 18] = __ldg(weff + (size_t)k0 * 18 + i);
+        __syncthreads();
+#pragma unroll 2
+        for (int kk = lane; kk < OH_KC; kk += 32) {
+            float v[OH_P];
 #pragma unroll
-            for (int ox = 0; ox < 3; ox++) {
-                const int ix = ox + kx - 1;
-                if (ix < 0 || ix > 7) continue;
-                const float v = f[ci * 64 + iy * 8 + ix];
-                acc[0][oy * 3 + ox] = fmaf(v, w0, acc[0][oy * 3 + ox]);
-                acc[1][oy * 3 + ox] = fmaf(v, w1, acc[1][oy * 3 + ox]);
-            }
+            for (int q = 0; q < OH_P; q++) v[q] = f[q][k0 + kk];
+            const float4* wr = reinterpret_cast<const float4*>(&s_w[kk][0]);
+            const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+            const float2 w4 = *reinterpret_cast<const float2*>(&s_w[kk][16]);
+            const float wv[18] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w, w4.x, w4.y};
+#pragma unroll
+            for (int q = 0; q < OH_P; q++)
+#pragma unroll
+                for (int o = 0; o < 18; o++) acc[q][o] = fmaf(v[q], wv[o], acc[q][o]);
         }
     }
-    float m0 = 0.f, m1 = 0.f;
 #pragma unroll
-    for (int q = 0; q < 9; q++) {
-        m0 += tanhf(warp_sum(acc[0][q]) + bias[0]);
-        m1 += tanhf(warp_sum(acc[1][q]) + bias[1]);
-    }
-    if (lane == 0) {
+    for (int q = 0; q < OH_P; q++) {
+        float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+        for (int o = 0; o < 9; o++) {
+            m0 += tanhf(warp_sum(acc[q][o]) + bias[0]);
+            m1 += tanhf(warp_sum(acc[q][9 + o]) + bias[1]);
+        }
+        const int pi = p0 + q;
+        if (lane != 0 || pi >= n) continue;
+        if (count != nullptr && (pi % group) >= count[pi / group]) continue;
         m0 /= 9.0f; m1 /= 9.0f;
         const float ang = atan2f(m0 + 1e-8f, m1 + 1e-8f);  // architectures.py:78
         if (angle_out) angle_out[pi] = ang;
         if (out) {
-            const float c = cosf(ang), s = sinf(ang);  // get_rotation_matrix, LAF.py:276-283
+            const float c = cosf(ang), sn = sinf(ang);  // get_rotation_matrix, LAF.py:276-283
             float* o = out + (size_t)pi * 4;
-            o[0] = c; o[1] = s; o[2] = -s; o[3] = c;
+            o[0] = c; o[1] = sn; o[2] = -sn; o[3] = c;
         }
     }
 }
@@ -335,7 +347,22 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
     } else {
         const int no = (kind == AG_NET_AFFNET) ? 3 : 2;
         const float* w = p; const float* bias = w + (size_t)no * c * 64;
-        packed.insert(packed.end(), w, w + (size_t)no * c * 64);
+        if (kind == AG_NET_ORINET) {
+            // w_eff[k = ci*64 + y*8 + x][ch*9 + oy*3 + ox] = w[ch][ci][y-oy+1][x-ox+1] (zero outside the 8x8 kernel): padding = 1
+            packed.resize(packed.size() + (size_t)4096 * 18);
+            float* dst = packed.data() + hw_off;
+            for (int ci = 0; ci < 64; ci++)
+                for (int y = 0; y < 8; y++)
+                    for (int x = 0; x < 8; x++)
+                        for (int ch = 0; ch < 2; ch++)
+                            for (int oy = 0; oy < 3; oy++)
+                                for (int ox = 0; ox < 3; ox++) {
+                                    const int ky = y - oy + 1, kx = x - ox + 1;
+                                    const float v = (ky >= 0 && ky < 8 && kx >= 0 && kx < 8) ? w[((size_t)ch * 64 + ci) * 64 + ky * 8 + kx] : 0.f;
+                                    dst[((size_t)ci * 64 + y * 8 + x) * 18 + ch * 9 + oy * 3 + ox] = v;
+                                }
+        } else
+            packed.insert(packed.end(), w, w + (size_t)no * c * 64);
         hb_off = packed.size();
         packed.insert(packed.end(), bias, bias + no);
         while (packed.size() % 4) packed.push_back(0.f);
@@ -522,7 +549,7 @@ static int orinet_impl(const ag_net_t* net, const float* d_patches, const tc::Fi
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = run_trunk(net, d_patches, src, n, group, d_count, a, b, &b, st))) return rc;
-    orinet_head_kernel<<<cdiv(n, 8), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, d_angle, n, group, d_count);
+    orinet_head_kernel<<<cdiv(n, OH_W * OH_P), OH_W * 32, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, d_angle, n, group, d_count);
     AG_CHECK_LAUNCH("orinet_head_kernel");
     return AG_OK;
 }

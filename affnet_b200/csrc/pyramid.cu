@@ -77,44 +77,102 @@ int make_taps(double sigma, BlurTaps* t) {
 }
 
 // ---- device: fused separable blur ---------------------------------------------------------------
-constexpr int TW = 64, TH = 32, NT = 256;
+// 64x64 output tile per CTA.  Both passes are register blocked so that shared memory is read with 128-bit loads:
+//   horizontal: one thread -> 4 adjacent outputs of a row from 4+2R inputs (ceil((4+2R)/4) LDS.128, 4*(2R+1) FMA)
+//   vertical  : one thread -> 4x4 outputs (4 rows of a column quad) from 4+2R rows of the intermediate (4+2R LDS.128)
+// The tile is written with 128-bit stores when the row pitch allows it, and the stride-2 decimated copy that seeds the next
+// octave (F.avg_pool2d(k=1, s=2), HandCraftedModules.py:47) comes from the same registers.
+constexpr int TW = 64, TH = 64, NT = 256;
+
+template <int R>
+struct BlurGeom {
+    static constexpr int IH = TH + 2 * R;                      // rows of the input window
+    static constexpr int IWQ = (TW + 2 * R + 3) / 4 + 1;       // float4 per input row (window start aligned down to 4)
+    static constexpr int IW = IWQ * 4;
+    static constexpr int NQ = (4 + 2 * R + 3) / 4 + 1;         // float4 a horizontal quad may touch (window start not aligned)
+    static constexpr size_t SMEM = sizeof(float) * ((size_t)IH * IW + (size_t)IH * TW);
+};
 
 template <int R>
 __global__ void __launch_bounds__(NT) blur_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                    float* __restrict__ dec, int h, int w, BlurTaps taps) {
-    constexpr int IW = TW + 2 * R, IH = TH + 2 * R;
-    __shared__ float s_in[IH][IW + 1];
-    __shared__ float s_mid[IH][TW];
+    using G = BlurGeom<R>;
+    extern __shared__ __align__(16) float smem_f[];
+    float* s_in = smem_f;                       // [IH][IW]; column c holds image column x0 - R4 + c, R4 = R rounded up to 4
+    float* s_mid = smem_f + G::IH * G::IW;      // [IH][TW]
+    constexpr int R4 = (R + 3) / 4 * 4;
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const float* img = in + (size_t)b * h * w;
-    // 1. load tile + halo with replicate (clamp) addressing
-    for (int i = threadIdx.x; i < IH * IW; i += NT) {
-        int ly = i / IW, lx = i - ly * IW;
-        int gy = clampi(y0 + ly - R, 0, h - 1), gx = clampi(x0 + lx - R, 0, w - 1);
-        s_in[ly][lx] = __ldg(img + (size_t)gy * w + gx);
+    // 1. input window with replicate (clamp) addressing
+    for (int i = threadIdx.x; i < G::IH * G::IW; i += NT) {
+        const int ly = i / G::IW, lx = i - ly * G::IW;
+        const int gy = clampi(y0 + ly - R, 0, h - 1), gx = clampi(x0 + lx - R4, 0, w - 1);
+        s_in[i] = __ldg(img + (size_t)gy * w + gx);
     }
     __syncthreads();
-    // 2. horizontal pass on all IH rows
-    for (int i = threadIdx.x; i < IH * TW; i += NT) {
-        int ly = i / TW, lx = i - ly * TW;
-        float acc = 0.f;
+    // 2. horizontal pass: quads of 4 outputs; inputs of output x live at columns (x + R4 - R) .. (x + R4 + R)
+    for (int i = threadIdx.x; i < G::IH * (TW / 4); i += NT) {
+        const int ly = i / (TW / 4), q = i - ly * (TW / 4);
+        constexpr int OFF = R4 - R;                                // 0..3
+        float v[G::NQ * 4];
+        const float4* row = reinterpret_cast<const float4*>(s_in + ly * G::IW + q * 4);
 #pragma unroll
-        for (int k = 0; k <= 2 * R; k++) acc = fmaf(taps.w[k], s_in[ly][lx + k], acc);
-        s_mid[ly][lx] = acc;
+        for (int j = 0; j < G::NQ; j++) {
+            const float4 t = row[j];
+            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        }
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k <= 2 * R; k++) {
+            const float wk = taps.w[k];
+            o.x = fmaf(wk, v[OFF + k], o.x); o.y = fmaf(wk, v[OFF + k + 1], o.y);
+            o.z = fmaf(wk, v[OFF + k + 2], o.z); o.w = fmaf(wk, v[OFF + k + 3], o.w);
+        }
+        *reinterpret_cast<float4*>(s_mid + ly * TW + q * 4) = o;
     }
     __syncthreads();
-    // 3. vertical pass + store (+ decimated copy)
+    // 3. vertical pass: 4 rows x 4 columns per thread
     const int h2 = (h + 1) >> 1, w2 = (w + 1) >> 1;
-    for (int i = threadIdx.x; i < TH * TW; i += NT) {
-        int ly = i / TW, lx = i - ly * TW;
-        int gy = y0 + ly, gx = x0 + lx;
-        if (gy >= h || gx >= w) continue;
-        float acc = 0.f;
+    const bool vec_ok = (w & 3) == 0;
+    {
+        const int q = threadIdx.x & 15, rb = threadIdx.x >> 4;     // column quad 0..15, row block 0..15 (4 rows each)
+        float4 acc[4];
 #pragma unroll
-        for (int k = 0; k <= 2 * R; k++) acc = fmaf(taps.w[k], s_mid[ly + k][lx], acc);
-        out[(size_t)b * h * w + (size_t)gy * w + gx] = acc;
-        if (dec != nullptr && ((gy | gx) & 1) == 0) dec[(size_t)b * h2 * w2 + (size_t)(gy >> 1) * w2 + (gx >> 1)] = acc;
+        for (int r = 0; r < 4; r++) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4 + 2 * R; k++) {
+            const float4 t = *reinterpret_cast<const float4*>(s_mid + (rb * 4 + k) * TW + q * 4);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int tap = k - r;
+                if (tap >= 0 && tap <= 2 * R) {
+                    const float wk = taps.w[tap];
+                    acc[r].x = fmaf(wk, t.x, acc[r].x); acc[r].y = fmaf(wk, t.y, acc[r].y);
+                    acc[r].z = fmaf(wk, t.z, acc[r].z); acc[r].w = fmaf(wk, t.w, acc[r].w);
+                }
+            }
+        }
+        const int gx = x0 + q * 4;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int gy = y0 + rb * 4 + r;
+            if (gy >= h || gx >= w) continue;
+            float* orow = out + (size_t)b * h * w + (size_t)gy * w + gx;
+            const float vals[4] = {acc[r].x, acc[r].y, acc[r].z, acc[r].w};
+            if (vec_ok) {
+                *reinterpret_cast<float4*>(orow) = acc[r];           // w % 4 == 0 -> gx + 3 < w and 16-byte aligned
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (gx + e < w) orow[e] = vals[e];
+            }
+            if (dec != nullptr && (gy & 1) == 0) {
+                float* drow = dec + (size_t)b * h2 * w2 + (size_t)(gy >> 1) * w2 + (gx >> 1);
+                drow[0] = vals[0];
+                if (gx + 2 < w) drow[1] = vals[2];
+            }
+        }
     }
 }
 
@@ -124,10 +182,17 @@ static int launch_blur(const float* in, float* out, float* dec, int B, int h, in
     if (rc != AG_OK) return rc;
     dim3 grid(cdiv(w, TW), cdiv(h, TH), B), block(NT);
     switch (taps.r) {
-#define AG_BLUR_CASE(R)                                                  \
-    case R:                                                              \
-        blur_kernel<R><<<grid, block, 0, st>>>(in, out, dec, h, w, taps); \
-        break;
+#define AG_BLUR_CASE(R)                                                                                                   \
+    case R: {                                                                                                             \
+        static bool configured = false;                                                                                   \
+        if (!configured) {                                                                                                \
+            rc = check_cuda(cudaFuncSetAttribute(blur_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BlurGeom<R>::SMEM), \
+                            "blur smem attr");                                                                            \
+            if (rc != AG_OK) return rc;                                                                                   \
+            configured = true;                                                                                            \
+        }                                                                                                                 \
+        blur_kernel<R><<<grid, block, BlurGeom<R>::SMEM, st>>>(in, out, dec, h, w, taps);                                  \
+    } break;
         AG_BLUR_CASE(1) AG_BLUR_CASE(2) AG_BLUR_CASE(3) AG_BLUR_CASE(4) AG_BLUR_CASE(5) AG_BLUR_CASE(6)
         AG_BLUR_CASE(7) AG_BLUR_CASE(8) AG_BLUR_CASE(9) AG_BLUR_CASE(10) AG_BLUR_CASE(11) AG_BLUR_CASE(12)
 #undef AG_BLUR_CASE
