@@ -225,13 +225,45 @@ def _main(real_stdout):
             dist.all_gather_into_tensor(gather[0], out[2]); dist.all_gather_into_tensor(gather[1], out[0]); dist.all_gather_into_tensor(gather[2], out[3])
         return out
 
+    # End-to-end leg: every step uploads ITS OWN batch from pinned host memory and downloads ITS OWN results.  Transfers run on
+    # a copy stream and are software-pipelined against the compute of the neighbouring steps (double-buffered device staging),
+    # as a serving loop would do; all of it is inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage_in = [torch.empty_like(dev_imgs) for _ in range(2)]
+    stage_out = [(torch.empty(B, K, 128, device=dev), torch.empty(B, K, 2, 3, device=dev), torch.empty(B, K, device=dev),
+                  torch.empty(B, dtype=torch.int32, device=dev)) for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"i": 0}
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            stage_in[slot].copy_(host_imgs, non_blocking=True)
+            ev_in[slot].record(copy_stream)
+
     def step_e2e():
-        x = host_imgs.to(dev, non_blocking=True)
-        out = pipe.replay(x) if use_graph else pipe.run(x)
+        i = e2e_state["i"]; slot = i & 1
+        cur = torch.cuda.current_stream()
+        if i == 0:
+            upload(slot)
+        upload_next = slot ^ 1
+        cur.wait_event(ev_in[slot])                       # this step's images are on the device
+        out = pipe.replay(stage_in[slot]) if use_graph else pipe.run(stage_in[slot])
         if world > 1:
             dist.all_gather_into_tensor(gather[0], out[2]); dist.all_gather_into_tensor(gather[1], out[0]); dist.all_gather_into_tensor(gather[2], out[3])
-        host_desc.copy_(out[2], non_blocking=True); host_lafs.copy_(out[0], non_blocking=True)
-        host_resp.copy_(out[1], non_blocking=True); host_cnt.copy_(out[3], non_blocking=True)
+        if i >= 2:
+            cur.wait_event(ev_done[slot])                 # the download that used this staging slot two steps ago has finished
+        so = stage_out[slot]
+        so[0].copy_(out[2], non_blocking=True); so[1].copy_(out[0], non_blocking=True); so[2].copy_(out[1], non_blocking=True); so[3].copy_(out[3], non_blocking=True)
+        ev_out[slot].record(cur)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_out[slot])
+            host_desc.copy_(so[0], non_blocking=True); host_lafs.copy_(so[1], non_blocking=True)
+            host_resp.copy_(so[2], non_blocking=True); host_cnt.copy_(so[3], non_blocking=True)
+            ev_done[slot].record(copy_stream)
+        upload(upload_next)                               # next step's images travel while this step computes
+        e2e_state["i"] = i + 1
 
     def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
@@ -263,7 +295,24 @@ def _main(real_stdout):
     total_ms, clocks = timed(step_device, args.steps, args.warmup, sampler)
     pipe.check()
     n_desc = int(pipe.count.sum().item())
-    e2e_ms, _ = timed(step_e2e, args.steps, args.warmup)
+    # e2e timing: ONE event pair around all K steps, closed only after the last step's results have reached host memory
+    for _ in range(args.warmup):
+        step_e2e()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.current_stream().wait_stream(copy_stream)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
 
     # ---- per-kernel CUDA-event profile of the same step (non-graph launch path), rank 0 ---------------------------
     roof = None
@@ -327,7 +376,7 @@ def _main(real_stdout):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic images (seeded noise, blur sigma 2, stretched), pretrained weights from tests/golden",
                 "config": {"workload": "%dx%d grayscale, %d kpts/img, batch of %d images per GPU per step (configs[1] tiled = configs[3] shard)" % (W, H, K, B),
-                           "do_ori": True, "border": 5, "mrSize": 5.192, "cuda_graph": use_graph, "l2": "256 MiB flush write between timed steps",
+                           "do_ori": True, "border": 5, "mrSize": 5.192, "cuda_graph": use_graph, "l2": "256 MiB flush write between timed steps (device-resident leg); e2e leg: fresh inputs arrive by DMA every step, no flush",
                            "parallelism": "images sharded across GPUs, NCCL all-gather of descriptors/LAFs/counts per step" if world > 1 else "single GPU"},
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "e2e": {"value": e2e_v, "unit": "Mpix/s", "h2d_bytes_per_step": B * H * W * 4,
