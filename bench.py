@@ -228,7 +228,8 @@ def _main(real_stdout):
     # End-to-end leg: every step uploads ITS OWN batch from pinned host memory and downloads ITS OWN results.  Transfers run on
     # a copy stream and are software-pipelined against the compute of the neighbouring steps (double-buffered device staging),
     # as a serving loop would do; all of it is inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream = torch.cuda.Stream(device=dev)     # device -> host
+    up_stream = torch.cuda.Stream(device=dev)       # host -> device (separate, so uploads never queue behind a download)
     stage_in = [torch.empty_like(dev_imgs) for _ in range(2)]
     stage_out = [(torch.empty(B, K, 128, device=dev), torch.empty(B, K, 2, 3, device=dev), torch.empty(B, K, device=dev),
                   torch.empty(B, dtype=torch.int32, device=dev)) for _ in range(2)]
@@ -238,17 +239,19 @@ def _main(real_stdout):
     e2e_state = {"i": 0}
 
     def upload(slot):
-        with torch.cuda.stream(copy_stream):
+        with torch.cuda.stream(up_stream):
             stage_in[slot].copy_(host_imgs, non_blocking=True)
-            ev_in[slot].record(copy_stream)
+            ev_in[slot].record(up_stream)
 
     def step_e2e():
         i = e2e_state["i"]; slot = i & 1
         cur = torch.cuda.current_stream()
         if i == 0:
             upload(slot)
-        upload_next = slot ^ 1
         cur.wait_event(ev_in[slot])                       # this step's images are on the device
+        ev_free = torch.cuda.Event(); ev_free.record(cur)
+        up_stream.wait_event(ev_free)                     # the other input slot was consumed by the previous step
+        upload(slot ^ 1)                                  # next step's images travel while this step computes
         out = pipe.replay(stage_in[slot]) if use_graph else pipe.run(stage_in[slot])
         if world > 1:
             dist.all_gather_into_tensor(gather[0], out[2]); dist.all_gather_into_tensor(gather[1], out[0]); dist.all_gather_into_tensor(gather[2], out[3])
@@ -262,7 +265,6 @@ def _main(real_stdout):
             host_desc.copy_(so[0], non_blocking=True); host_lafs.copy_(so[1], non_blocking=True)
             host_resp.copy_(so[2], non_blocking=True); host_cnt.copy_(so[3], non_blocking=True)
             ev_done[slot].record(copy_stream)
-        upload(upload_next)                               # next step's images travel while this step computes
         e2e_state["i"] = i + 1
 
     def timed(fn, steps, warmup, sampler=None):
@@ -307,6 +309,7 @@ def _main(real_stdout):
     for _ in range(args.steps):
         step_e2e()
     torch.cuda.current_stream().wait_stream(copy_stream)
+    torch.cuda.current_stream().wait_stream(up_stream)
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
