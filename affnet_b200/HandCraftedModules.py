@@ -45,3 +45,57 @@ class HessianResp(nn.Module):
         out = torch.empty_like(x)
         L.check(L.lib().ag_hessian_response(L.ptr(x), L.ptr(out), x.size(0) * x.size(1), x.size(2), x.size(3), float(scale), 0.0, L.stream_ptr()))
         return out
+
+
+def _gauss_window(PS, sigma, scale, device):
+    """CircularGaussKernel(kernlen=PS, sigma=sigma) * scale as a device tensor (Utils.py:92-114)."""
+    import numpy as np
+    buf = np.empty(PS * PS, np.float32)
+    L.check(L.lib().ag_circular_gauss_kernel(PS, float(sigma) if sigma else 0.0, buf.ctypes.data_as(C.c_void_p)))
+    return (torch.from_numpy(buf) * scale).to(device)
+
+
+class OrientationDetector(nn.Module):
+    """HandCraftedModules.py:133-192: dominant gradient orientation of a PS x PS patch (36 bins)."""
+
+    def __init__(self, mrSize=3.0, patch_size=None):
+        super().__init__()
+        self.PS = 32 if patch_size is None else patch_size
+        self.mrSize = mrSize
+        self.num_ang_bins = 36
+        self._gk = None
+
+    def forward(self, x, return_rot_matrix=False):
+        x = L.f32c(x, "patches")
+        if x.dim() != 4 or x.size(1) != 1 or x.size(2) != self.PS or x.size(3) != self.PS:
+            raise L.AffnetB200Error("expected patches of shape [n,1,%d,%d]" % (self.PS, self.PS))
+        if self._gk is None or self._gk.device != x.device:
+            self._gk = _gauss_window(self.PS, None, 10.0, x.device)
+        n = x.size(0)
+        ang = torch.empty(n, dtype=torch.float32, device=x.device)
+        L.check(L.lib().ag_orientation_hist(L.ptr(x), n, self.PS, L.ptr(self._gk), L.ptr(ang), L.stream_ptr()))
+        if return_rot_matrix:
+            c, s = torch.cos(ang).view(-1, 1, 1), torch.sin(ang).view(-1, 1, 1)
+            return torch.cat([torch.cat([c, s], dim=2), torch.cat([-s, c], dim=2)], dim=1)
+        return ang
+
+
+class AffineShapeEstimator(nn.Module):
+    """HandCraftedModules.py:81-132: one Baumberg step (second-moment matrix -> A), up-is-up rectified."""
+
+    def __init__(self, threshold=0.001, patch_size=19):
+        super().__init__()
+        self.threshold = threshold
+        self.PS = patch_size
+        self._gk = None
+
+    def forward(self, x, *unused):
+        x = L.f32c(x, "patches")
+        if x.dim() != 4 or x.size(1) != 1 or x.size(2) != self.PS or x.size(3) != self.PS:
+            raise L.AffnetB200Error("expected patches of shape [n,1,%d,%d]" % (self.PS, self.PS))
+        if self._gk is None or self._gk.device != x.device:
+            self._gk = _gauss_window(self.PS, (self.PS / 2) / 3.0, 1.0, x.device)
+        n = x.size(0)
+        A = torch.empty(n, 2, 2, dtype=torch.float32, device=x.device)
+        L.check(L.lib().ag_baumberg_shape(L.ptr(x), n, self.PS, L.ptr(self._gk), L.ptr(A), L.stream_ptr()))
+        return A

@@ -4,8 +4,8 @@ affine patch sampling -> AffNet -> shape filter -> (OriNet) -> denormalised LAFs
 
 Differences from the reference that a caller can observe: nothing is printed; inputs must be CUDA tensors (there
 is no CPU path); `pyr_idxs` / `level_idxs` may be given as float or int tensors (returned as float, as the
-reference does).  The hand-crafted fallbacks used when AffNet/OriNet are None (Baumberg iteration, gradient
-histogram orientation) are not part of this hot path and raise NotImplementedError.
+reference does).  AffNet=None / OriNet=None select the hand-crafted estimators (Baumberg step, gradient-histogram
+orientation) exactly as the reference does; a custom RespNet is not supported.
 """
 import ctypes as C
 
@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .HandCraftedModules import ScalePyramid
+from .HandCraftedModules import AffineShapeEstimator, OrientationDetector, ScalePyramid
 from .LAF import denormalizeLAFs, get_pyramid_and_level_index_for_LAFs, normalizeLAFs
 
 
@@ -41,8 +41,9 @@ class ScaleSpaceAffinePatchExtractor(nn.Module):
             self.th = 0
         if RespNet is not None:
             raise NotImplementedError("custom RespNet: only the fused Hessian response is implemented")
-        self.OriNet = OriNet
-        self.AffNet = AffNet
+        # SparseImgRepresenter.py:42-49: the hand-crafted estimators are the defaults
+        self.OriNet = OriNet if OriNet is not None else OrientationDetector(patch_size=19)
+        self.AffNet = AffNet if AffNet is not None else AffineShapeEstimator(patch_size=19)
         self.ScalePyrGen = ScalePyramid(nLevels=nlevels, init_sigma=init_sigma, border=border)
         self._plan = None
         self._pyr_buf = None
@@ -140,8 +141,6 @@ class ScaleSpaceAffinePatchExtractor(nn.Module):
     # ---- affine shape -------------------------------------------------------------------------------------------
     def getAffineShape(self, final_resp, LAFs, final_pyr_idxs, final_level_idxs, num_features=0):
         """SparseImgRepresenter.py:113-165."""
-        if self.AffNet is None:
-            raise NotImplementedError("AffNet=None (Baumberg iteration) is outside the accelerated hot path")
         n = LAFs.size(0)
         dev = LAFs.device
         LAFs = L.f32c(LAFs)
@@ -177,8 +176,6 @@ class ScaleSpaceAffinePatchExtractor(nn.Module):
     # ---- orientation --------------------------------------------------------------------------------------------
     def getOrientation(self, LAFs, final_pyr_idxs, final_level_idxs):
         """SparseImgRepresenter.py:167-180 (without the reference's discarded second extraction)."""
-        if self.OriNet is None:
-            raise NotImplementedError("OriNet=None (gradient-histogram orientation) is outside the accelerated hot path")
         patches = self._patches(LAFs, final_pyr_idxs, final_level_idxs, self.OriNet.PS)
         angles = self.OriNet(patches)
         R = angles if angles.dim() > 2 else angles2A(angles).view(-1, 2, 2)

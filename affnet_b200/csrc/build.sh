@@ -16,6 +16,8 @@ for f in "$HERE"/*.cu; do
     pids+=($!)
   fi
 done
-for p in "${pids[@]}"; do wait $p; done
+fail=0
+for p in "${pids[@]}"; do wait $p || fail=1; done
+if [ $fail = 1 ]; then echo "build failed" >&2; rm -f "$HERE"/obj/*.o.failed; for l in "$HERE"/obj/*.o.log; do grep -l "error" "$l" >/dev/null 2>&1 && rm -f "${l%.log}"; done; exit 1; fi
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libaffnet_b200.so" "$HERE"/obj/*.o -lcudart
 echo "built $OUT/libaffnet_b200.so"

@@ -208,6 +208,20 @@ int ag_lafs_apply_rotation(float* d_lafs, const float* d_R, int n, void* stream)
 int ag_lafs_scale(const float* d_in, float* d_out, int n, float a_coef, float x_coef, float y_coef, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Hand-crafted estimators (SURVEY.md §8f "next" rows): what the reference uses when OriNet / AffNet are None.
+ *   ag_orientation_hist  replaces OrientationDetector.forward   (HandCraftedModules.py:133-192): 36-bin gradient histogram,
+ *                        (0.33,0.34,0.33) smoothing, arg-max -> angle [n]
+ *   ag_baumberg_shape    replaces AffineShapeEstimator.forward  (HandCraftedModules.py:81-132): second-moment matrix ->
+ *                        inverse square root -> up-is-up rectified A [n,2,2]
+ * d_patches [n,PS,PS] (3 <= PS <= 41); d_gk [PS,PS] = the module's Gaussian window: ag_circular_gauss_kernel(PS, sigma, h_out)
+ * reproduces CircularGaussKernel (Utils.py:92-114; sigma <= 0 selects the default sigma^2 = 0.9 (PS/2)^2 / 2); the orientation
+ * window is 10x that kernel, the Baumberg window uses sigma = (PS/2)/3.
+ * ------------------------------------------------------------------------------------------ */
+int ag_circular_gauss_kernel(int kernlen, double sigma, float* h_out);
+int ag_orientation_hist(const float* d_patches, int n, int PS, const float* d_gk, float* d_angle, void* stream);
+int ag_baumberg_shape(const float* d_patches, int n, int PS, const float* d_gk, float* d_A, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Batched end-to-end pipeline (new; the reference processes one image at a time):
  * pyramid -> detect -> select(1.5K) -> sample -> AffNet -> filter(K) -> [sample -> OriNet -> rotate]
  * -> denormalise -> level select -> sample -> HardNet.       = ScaleSpaceAffinePatchExtractor.forward

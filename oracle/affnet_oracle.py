@@ -557,3 +557,76 @@ def random_state_dict(kind, seed):
         sd["features.19.weight"] = torch.randn(nout, c, 8, 8, generator=g) * (0.5 / math.sqrt(64 * c))
         sd["features.19.bias"] = torch.full((nout,), 0.01)
     return sd
+
+
+# ----------------------------------------------------------------------------------------------
+# §8(f) "next" rows: hand-crafted orientation and Baumberg affine shape   HandCraftedModules.py:81-192
+# ----------------------------------------------------------------------------------------------
+
+
+def circular_gauss_kernel(kernlen, sigma=None):
+    """CircularGaussKernel(kernlen=..., sigma=...) with circ_zeros=False, norm=True (Utils.py:92-114), float64."""
+    half = kernlen / 2
+    r2 = float(half * half)
+    sigma2 = 0.9 * r2 if sigma is None else 2.0 * sigma * sigma
+    x = np.linspace(-half, half, kernlen)
+    xv, yv = np.meshgrid(x, x, sparse=False, indexing="xy")
+    k = np.exp(-((xv ** 2 + yv ** 2) / sigma2))
+    return k / np.sum(k)
+
+
+def orientation_hist(patches, num_bins=36):
+    """OrientationDetector.forward (HandCraftedModules.py:168-192), returns the angle [n].
+    gx/gy = (0.5,0,-0.5) cross-correlations with replicate padding; only the lower-bin weight wo0 is accumulated (as the
+    reference does); smoothing (0.33,0.34,0.33) with ZERO padding; argmax; angle = -(2 pi idx/36 - pi)."""
+    PS = patches.size(2)
+    x = patches
+    xp = F.pad(x, (1, 1, 0, 0), "replicate")
+    gx = 0.5 * xp[:, :, :, :-2] - 0.5 * xp[:, :, :, 2:]
+    yp = F.pad(x, (0, 0, 1, 1), "replicate")
+    gy = 0.5 * yp[:, :, :-2, :] - 0.5 * yp[:, :, 2:, :]
+    gk = 10.0 * torch.from_numpy(circular_gauss_kernel(PS).astype(np.float32))
+    mag = torch.sqrt(gx * gx + gy * gy + 1e-10) * gk
+    ori = torch.atan2(gy, gx)
+    o_big = float(num_bins) * (ori + 1.0 * math.pi) / (2.0 * math.pi)
+    bo0 = torch.floor(o_big)
+    wo1 = o_big - bo0
+    bo0 = bo0 % num_bins
+    wo0 = (1.0 - wo1) * mag
+    bins = torch.stack([((bo0 == i).float() * wo0).mean(dim=(1, 2, 3)) for i in range(num_bins)], dim=1)   # [n,36]
+    sm = F.conv1d(bins.view(-1, 1, num_bins), torch.tensor([[[0.33, 0.34, 0.33]]]), padding=1).view(-1, num_bins)
+    idx = sm.max(1)[1]
+    return -((2.0 * float(np.pi) * idx.float() / float(num_bins)) - float(math.pi))
+
+
+def baumberg_shape(patches):
+    """AffineShapeEstimator.forward (HandCraftedModules.py:94-132): second-moment matrix -> inverse square root -> up-is-up."""
+    PS = patches.size(2)
+    x = patches
+    xp = F.pad(x, (1, 1, 0, 0), "replicate")
+    gx = xp[:, :, :, 2:] - xp[:, :, :, :-2]
+    yp = F.pad(x, (0, 0, 1, 1), "replicate")
+    gy = yp[:, :, 2:, :] - yp[:, :, :-2, :]
+    gk = torch.from_numpy(circular_gauss_kernel(PS, sigma=(PS / 2) / 3.0).astype(np.float32))
+    a = (gx * gx * gk).view(x.size(0), -1).mean(dim=1)
+    b = (gx * gy * gk).view(x.size(0), -1).mean(dim=1)
+    c = (gy * gy * gk).view(x.size(0), -1).mean(dim=1)
+    eps = 1e-12
+    mask = (b != 0).float()
+    r1 = mask * (c - a) / (2.0 * b + eps)
+    t1 = torch.sign(r1) / (torch.abs(r1) + torch.sqrt(1.0 + r1 * r1))
+    r = 1.0 / torch.sqrt(1.0 + t1 * t1)
+    t = t1 * r
+    r = r * mask + 1.0 * (1.0 - mask)
+    t = t * mask
+    xx = 1.0 / torch.sqrt(r * r * a - 2.0 * r * t * b + t * t * c)
+    zz = 1.0 / torch.sqrt(t * t * a + 2.0 * r * t * b + r * r * c)
+    d = torch.sqrt(xx * zz)
+    xx = xx / d
+    zz = zz / d
+    na = r * r * xx + t * t * zz
+    nb = -r * t * xx + t * r * zz
+    nc = t * t * xx + r * r * zz
+    A = torch.zeros(x.size(0), 2, 2)
+    A[:, 0, 0] = na; A[:, 0, 1] = nb; A[:, 1, 0] = nb; A[:, 1, 1] = nc
+    return rectify_up_is_up(A)

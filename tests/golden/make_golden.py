@@ -13,6 +13,7 @@ changes.  Outputs (all .npz, compressed):
   nms_q4.npz         NMS3dAndComposeA on synthetic response maps with a non-trivial octave map (Q4)
   face_patches.npz   first 64 patches of examples/just_shape/img/face.png -> AffNetFast matrices
   nets_random.npz    the three nets on 32 random patches (input + outputs)
+  handcrafted.npz    OrientationDetector / AffineShapeEstimator on 19x19 patches; default detector (OriNet=None) end to end
 """
 import contextlib
 import io
@@ -142,6 +143,22 @@ def main():
     with torch.no_grad():
         A = aff(P)
     save("face_patches.npz", patches_u8=pts, A=A)
+
+    # ---------------- hand-crafted estimators ---------------------------
+    import torch.nn.functional as F2  # noqa: F401
+    crop_img = gray_of(crop)
+    # NB: the reference's own Baumberg loop (AffNet=None, num_Baum_iters > 0) raises TypeError under python3 because
+    # batched_forward passes a stray dict to AffineShapeEstimator.forward (Utils.py:54,66); only the module itself is runnable.
+    det0 = m["SparseImgRepresenter"].ScaleSpaceAffinePatchExtractor(mrSize=5.192, num_features=300, border=5, num_Baum_iters=0)
+    with torch.no_grad(), quiet():
+        dL0, r0 = det0(crop_img, do_ori=True)       # detector + gradient-histogram orientation (OriNet=None default)
+        resp, LAFs, pidx, lidx = det0.multiScaleDetector(crop_img, 450)
+        L2 = LAFs.clone(); L2[:, 0:2, 0:2] = det0.mrSize * L2[:, :, 0:2]
+        inv = m["LAF"].get_inverted_pyr_index(det0.scale_pyr, pidx, lidx)
+        P19 = m["LAF"].extract_patches_from_pyramid_with_inv_index(det0.scale_pyr, inv, L2, PS=19)
+        od = m["HandCraftedModules"].OrientationDetector(patch_size=19)
+        ae = m["HandCraftedModules"].AffineShapeEstimator(patch_size=19)
+        save("handcrafted.npz", patches19=P19[:200], angle=od(P19[:200]), A=ae(P19[:200]), default_dLAFs=dL0, default_resp=r0)
 
     # ---------------- nets on random patches ----------------------------------------------
     P = torch.rand(32, 1, 32, 32, generator=g) * 255.0

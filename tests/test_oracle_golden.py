@@ -148,3 +148,11 @@ def test_end_to_end_graf_full_known_answers():
     assert (T(z["noori_desc"]).float()[ia] - desc[ib]).abs().max() < 5e-3
     # candidate counts per (octave, level): 7885 in total
     assert int(z["cand_counts"].sum()) == 7885
+
+
+def test_handcrafted_estimators_8f():
+    """gradient-histogram orientation and the Baumberg step against the reference's outputs."""
+    z = gold("handcrafted.npz")
+    P = T(z["patches19"])
+    assert torch.equal(O.orientation_hist(P), T(z["angle"]))
+    assert (O.baumberg_shape(P) - T(z["A"])).abs().max() < 1e-6
