@@ -85,6 +85,9 @@ PROTOTYPES = {
     "ag_circular_gauss_kernel": (i32, [i32, f64, vp]),
     "ag_orientation_hist": (i32, [vp, i32, i32, vp, vp, vp]),
     "ag_baumberg_shape": (i32, [vp, i32, i32, vp, vp, vp]),
+    "ag_distance_matrix": (i32, [vp, i32, vp, i32, i32, vp, vp]),
+    "ag_match_snn_workspace_bytes": (sz, [i32, i32]),
+    "ag_match_snn": (i32, [vp, i32, vp, i32, i32, f32, vp, sz, vp, vp, vp, vp, vp]),
     "ag_pipeline_create": (i32, [C.POINTER(PipelineConfig), vp, vp, vp, C.POINTER(vp)]),
     "ag_pipeline_destroy": (None, [vp]),
     "ag_pipeline_workspace_bytes": (sz, [vp]),

@@ -630,3 +630,20 @@ def baumberg_shape(patches):
     A = torch.zeros(x.size(0), 2, 2)
     A[:, 0, 0] = na; A[:, 0, 1] = nb; A[:, 1, 0] = nb; A[:, 1, 1] = nc
     return rectify_up_is_up(A)
+
+
+def distance_matrix_vector(anchor, positive):
+    """Losses.py:5-13."""
+    d1 = torch.sum(anchor * anchor, dim=1).unsqueeze(-1)
+    d2 = torch.sum(positive * positive, dim=1).unsqueeze(-1)
+    return torch.sqrt((d1.repeat(1, positive.size(0)) + torch.t(d2.repeat(1, anchor.size(0))) - 2.0 * torch.mm(anchor, positive.t())) + 1e-6)
+
+
+def match_snn(desc1, desc2, ratio=0.8):
+    """train_AffNet_test_on_graffity.py:292-298: -> (idx_in_1, idx_in_2, min_dist, second_dist)."""
+    dist = distance_matrix_vector(desc1, desc2)
+    mn, idx2 = torch.min(dist, 1)
+    dist[:, idx2] = 100000
+    sec, _ = torch.min(dist, 1)
+    mask = (mn / (sec + 1e-8)) <= ratio
+    return torch.arange(idx2.size(0))[mask], idx2[mask], mn, sec

@@ -380,3 +380,20 @@ def test_handcrafted_estimators_8f(L):
     det16 = ScaleSpaceAffinePatchExtractor(mrSize=5.192, num_features=300, border=5, num_Baum_iters=16)
     dL16, r16 = det16(img.to(DEV), do_ori=True)
     assert 0 < dL16.shape[0] <= 300 and bool(torch.isfinite(dL16).all())
+
+
+def test_snn_matcher_8f(L, nets):
+    """distance_matrix_vector + SNN ratio test on real descriptors of two views."""
+    from affnet_b200.Losses import distance_matrix_vector, match_snn
+    aff, ori, hn = nets
+    g = torch.Generator().manual_seed(21)
+    d1 = torch.nn.functional.normalize(torch.randn(700, 128, generator=g), dim=1)
+    d2 = torch.cat([torch.nn.functional.normalize(d1[:400] + 0.25 * torch.randn(400, 128, generator=g), dim=1),
+                    torch.nn.functional.normalize(torch.randn(333, 128, generator=g), dim=1)])
+    D = distance_matrix_vector(d1.to(DEV), d2.to(DEV)).cpu()
+    assert (D - O.distance_matrix_vector(d1, d2)).abs().max() < 1e-5
+    i1, i2, mn, sec = match_snn(d1.to(DEV), d2.to(DEV), 0.8)
+    o1, o2, omn, osec = O.match_snn(d1, d2, 0.8)
+    assert (mn.cpu() - omn).abs().max() < 1e-5 and (sec.cpu() - osec).abs().max() < 1e-5
+    assert torch.equal(i1.cpu(), o1) and torch.equal(i2.cpu(), o2)
+    assert 300 < i1.numel() <= 400

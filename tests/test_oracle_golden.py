@@ -156,3 +156,16 @@ def test_handcrafted_estimators_8f():
     P = T(z["patches19"])
     assert torch.equal(O.orientation_hist(P), T(z["angle"]))
     assert (O.baumberg_shape(P) - T(z["A"])).abs().max() < 1e-6
+
+
+def test_distance_matrix_vs_reference_if_present():
+    """Losses.distance_matrix_vector against the live reference when /root/reference is mounted."""
+    import ref_harness as R
+    if not R.available():
+        pytest.skip("reference tree not present")
+    import importlib, sys
+    R.ref_modules()
+    ref = importlib.import_module("Losses")
+    g = torch.Generator().manual_seed(5)
+    a, b = torch.randn(50, 128, generator=g), torch.randn(70, 128, generator=g)
+    assert torch.equal(O.distance_matrix_vector(a, b), ref.distance_matrix_vector(a, b))
