@@ -41,3 +41,29 @@ def test_other_configs(nets, B, H, Wd, K, border, n_oct):
         assert (desc[b, :n].norm(dim=1) - 1).abs().max() < 1e-4
         c = lafs[b, :n, :, 2]
         assert bool((c[:, 0] >= 0).all() and (c[:, 0] <= Wd).all() and (c[:, 1] >= 0).all() and (c[:, 1] <= H).all())
+
+
+def test_edge_cases(nets):
+    """Empty / tiny / under-populated inputs: no crash, no stale rows, counts consistent with the oracle."""
+    from affnet_b200.SparseImgRepresenter import ScaleSpaceAffinePatchExtractor
+    from affnet_b200.pipeline import DetectDescribePipeline
+    aff, ori, hn = nets
+    # constant image: no maxima at any level (the reference raises on torch.cat([]); we return empty tensors)
+    flat = torch.full((1, 1, 96, 128), 77.0).cuda()
+    det = ScaleSpaceAffinePatchExtractor(mrSize=5.192, num_features=100, border=5, num_Baum_iters=1, AffNet=aff, OriNet=ori)
+    dL, r = det(flat, do_ori=True)
+    assert dL.shape == (0, 2, 3) and r.shape == (0,)
+    assert hn(det.extract_patches_from_pyr(dL, PS=32)).shape == (0, 128)
+    pipe = DetectDescribePipeline(2, 96, 128, aff, hn, ori, num_features=100, do_ori=True)
+    imgs = torch.cat([flat, O.synthetic_image(96, 128, 3).cuda()])
+    lafs, resp, desc, cnt = pipe.run(imgs)
+    pipe.check()
+    assert int(cnt[0]) == 0 and int(cnt[1]) > 0
+    # fewer candidates than requested: everything that survives is returned, in the oracle's order
+    small = O.synthetic_image(64, 80, 9)
+    det = ScaleSpaceAffinePatchExtractor(mrSize=5.192, num_features=5000, border=5, num_Baum_iters=1, AffNet=aff, OriNet=ori)
+    dL, r = det(small.cuda(), do_ori=False)
+    oL, oresp, st = O.detect(small, W["affnet"], None, 5000, do_ori=False)
+    assert abs(dL.shape[0] - oL.shape[0]) <= 2 and dL.shape[0] < 5000
+    if dL.shape[0] == oL.shape[0]:
+        assert (dL.cpu()[:, :, 2] - oL[:, :, 2]).abs().max() < 0.05          # same order (octave, level, raster), same places
