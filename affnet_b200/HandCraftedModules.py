@@ -73,7 +73,8 @@ class OrientationDetector(nn.Module):
             self._gk = _gauss_window(self.PS, None, 10.0, x.device)
         n = x.size(0)
         ang = torch.empty(n, dtype=torch.float32, device=x.device)
-        L.check(L.lib().ag_orientation_hist(L.ptr(x), n, self.PS, L.ptr(self._gk), L.ptr(ang), L.stream_ptr()))
+        if n:
+            L.check(L.lib().ag_orientation_hist(L.ptr(x), n, self.PS, L.ptr(self._gk), L.ptr(ang), L.stream_ptr()))
         if return_rot_matrix:
             c, s = torch.cos(ang).view(-1, 1, 1), torch.sin(ang).view(-1, 1, 1)
             return torch.cat([torch.cat([c, s], dim=2), torch.cat([-s, c], dim=2)], dim=1)
@@ -97,5 +98,6 @@ class AffineShapeEstimator(nn.Module):
             self._gk = _gauss_window(self.PS, (self.PS / 2) / 3.0, 1.0, x.device)
         n = x.size(0)
         A = torch.empty(n, 2, 2, dtype=torch.float32, device=x.device)
-        L.check(L.lib().ag_baumberg_shape(L.ptr(x), n, self.PS, L.ptr(self._gk), L.ptr(A), L.stream_ptr()))
+        if n:
+            L.check(L.lib().ag_baumberg_shape(L.ptr(x), n, self.PS, L.ptr(self._gk), L.ptr(A), L.stream_ptr()))
         return A

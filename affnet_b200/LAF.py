@@ -30,6 +30,8 @@ def extract_patches(img, LAFs, PS=32, bs=32):
 def _scale(LAFs, ac, xc, yc):
     LAFs = L.f32c(LAFs, "LAFs")
     out = torch.empty_like(LAFs)
+    if LAFs.size(0) == 0:
+        return out
     L.check(L.lib().ag_lafs_scale(L.ptr(LAFs), L.ptr(out), LAFs.size(0), ac, xc, yc, L.stream_ptr()))
     return out
 
@@ -54,6 +56,8 @@ def get_pyramid_and_level_index_for_LAFs(dLAFs, plan, PS):
     n = dLAFs.size(0)
     o = torch.empty(n, dtype=torch.int32, device=dLAFs.device)
     l = torch.empty(n, dtype=torch.int32, device=dLAFs.device)
+    if n == 0:
+        return o, l
     L.check(L.lib().ag_pyramid_level_for_lafs(C.byref(plan), L.ptr(dLAFs), n, PS, L.ptr(o), L.ptr(l), L.stream_ptr()))
     return o, l
 
