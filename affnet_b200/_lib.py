@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libaffnet_b200.so")
 AG_MAX_OCTAVES, AG_MAX_LEVELS = 16, 8
 NET_AFFNET, NET_ORINET, NET_HARDNET = 0, 1, 2
-ENGINE_SIMT, ENGINE_TC = 0, 1
+ENGINE_SIMT, ENGINE_TC, ENGINE_TC_EXACT = 0, 1, 2
 
 
 class AffnetB200Error(RuntimeError):

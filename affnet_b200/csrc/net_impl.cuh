@@ -7,6 +7,7 @@
 
 #define AG_ENGINE_SIMT 0  /* exact fp32 direct convolution */
 #define AG_ENGINE_TC 1    /* tcgen05: fp16 operands, fp32 accumulate; layer 1 and heads in fp32 */
+#define AG_ENGINE_TC_EXACT 2 /* tcgen05 with fp16 residual planes of weights AND activations (what OriNet always uses) */
 
 struct ag_net {
     int kind;

@@ -436,7 +436,8 @@ void ag_net_destroy(ag_net_t* net) {
 
 int ag_net_set_engine(ag_net_t* net, int engine) {
     AG_REQUIRE(net != nullptr, "NULL net");
-    AG_REQUIRE(engine == AG_ENGINE_SIMT || engine == AG_ENGINE_TC, "unknown engine");
+    AG_REQUIRE(engine == AG_ENGINE_SIMT || engine == AG_ENGINE_TC || engine == AG_ENGINE_TC_EXACT, "unknown engine");
+    AG_REQUIRE(engine != AG_ENGINE_TC_EXACT || net->kind != AG_NET_HARDNET, "the exact tensor-core engine exists for AffNet / OriNet");
     net->engine = engine;
     return AG_OK;
 }
@@ -449,7 +450,7 @@ size_t ag_net_workspace_bytes(int kind, int n) {
     const size_t simt = 2 * align_up((size_t)n * per * sizeof(float), 256);
     // tensor-core engine: two fp16 ping-pong buffers + fp32 features (AffNet/OriNet) or the fp16 head operand (HardNet, padded
     // to a multiple of 128 patches)
-    const size_t tcb = 2 * align_up((size_t)n * tc_act_bytes(kind), 256) +
+    const size_t tcb = 2 * align_up((size_t)n * tc_act_bytes(kind == AG_NET_AFFNET ? AG_NET_ORINET : kind), 256) +
                        (kind == AG_NET_HARDNET ? align_up(((size_t)n + 128) * 8192 * 2, 256) : align_up((size_t)n * 64 * 64 * sizeof(float), 256));
     return simt > tcb ? simt : tcb;
 }
@@ -485,12 +486,12 @@ static int trunk_hardnet(const ag_net* net, const float* patches, int n, int gro
 // Runs the six conv layers with the net's engine; *feat receives the fp32 NCHW feature pointer ([n,C,8,8]).
 static int run_trunk(const ag_net* net, const float* patches, const tc::FirstSrc* pyr_src, int n, int group, const int* count, float* a,
                      float* b, float** feat, cudaStream_t st) {
-    if (net->engine == AG_ENGINE_TC) {
+    if (net->engine != AG_ENGINE_SIMT) {
         const tc::FirstSrc src = pyr_src ? *pyr_src : tc_src_patches(patches);
         // the workspace [a, a + 2*(b-a)) is re-carved as [bufA | bufB | fp32 features]
         char* base = (char*)a;
         const size_t total = 2 * (size_t)((char*)b - (char*)a);
-        const size_t act = align_up((size_t)n * tc_act_bytes(net->kind), 256);
+        const size_t act = align_up((size_t)n * tc_act_bytes(net->engine == AG_ENGINE_TC_EXACT ? AG_NET_ORINET : net->kind), 256);
         const size_t fbytes = (size_t)n * 64 * 64 * sizeof(float);
         if (2 * act + fbytes > total) { set_error("tensor-core workspace too small"); return AG_ERR_CAPACITY; }
         void* bufA = base;
@@ -498,7 +499,7 @@ static int run_trunk(const ag_net* net, const float* patches, const tc::FirstSrc
         b = (float*)(base + 2 * act);
         *feat = b;
         if (net->kind == AG_NET_HARDNET) { set_error("HardNet tensor-core path has its own entry"); return AG_ERR_INVALID; }
-        if (net->kind == AG_NET_ORINET) return tc_trunk_orinet(net, src, n, group, count, bufA, bufB, b, st);
+        if (net->kind == AG_NET_ORINET || net->engine == AG_ENGINE_TC_EXACT) return tc_trunk_orinet(net, src, n, group, count, bufA, bufB, b, st);
         return tc_trunk_affnet(net, src, n, group, count, bufA, bufB, b, st);
     }
     *feat = b;
@@ -597,7 +598,7 @@ int ag_net_forward_pyr(const ag_net_t* net, const ag_pyramid_plan_t* plan, const
                        const int* d_lvl, const int* d_count, int cap, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
     AG_REQUIRE(net && plan && d_pyr && d_lafs && d_oct && d_lvl && d_out, "NULL argument");
     AG_REQUIRE(cap >= 1, "bad capacity");
-    AG_REQUIRE(net->engine == AG_ENGINE_TC, "fused sampling needs the tensor-core engine");
+    AG_REQUIRE(net->engine != AG_ENGINE_SIMT, "fused sampling needs a tensor-core engine");
     const tc::FirstSrc src = tc_src_pyramid(plan, d_pyr, d_lafs, d_oct, d_lvl, cap);
     const int n = plan->B * cap;
     if (net->kind == AG_NET_AFFNET) return affnet_impl(net, nullptr, &src, n, d_count, cap, d_out, d_ws, ws_bytes, stream);

@@ -165,7 +165,8 @@ void ag_net_destroy(ag_net_t* net);
 size_t ag_net_blob_floats(int kind);
 /* Compute engine of the six 3x3 conv layers: 0 = exact fp32 SIMT, 1 = tcgen05 tensor cores (fp16 operands, fp32
  * accumulation; the K=9 first layer and the 8x8 head stay fp32; AffNet adds the fp16 residual of the weights,
- * OriNet the residuals of weights and activations: fp32-grade results).  Default: 1 for all three nets. */
+ * OriNet the residuals of weights and activations: fp32-grade results); 2 = as 1 but AffNet also carries the activation
+ * residuals (fp32-grade A matrices at twice the activation traffic).  Default: 1 for all three nets. */
 int ag_net_set_engine(ag_net_t* net, int engine);
 int ag_net_get_engine(const ag_net_t* net);
 /* Scratch bytes for a forward over n patches. */

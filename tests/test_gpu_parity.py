@@ -231,6 +231,15 @@ def test_nets_vs_oracle(L, nets, engine):
     finally:
         aff.set_engine(L.ENGINE_TC); ori.set_engine(L.ENGINE_TC); hn.set_engine(L.ENGINE_TC)
     assert aff(torch.empty(0, 1, 32, 32, device=DEV)).shape == (0, 2, 2)
+    if engine == "tc":   # exact tensor-core engine for AffNet: fp32-grade A
+        try:
+            aff.set_engine(L.ENGINE_TC_EXACT)
+            P = sets[0]
+            dA = (aff(P.to(DEV)).cpu() - O.affnet_forward(P, W["affnet"])).abs().max().item()
+            print("engine tc-exact: max|dA| %.2e" % dA)
+            assert dA < 2e-5
+        finally:
+            aff.set_engine(L.ENGINE_TC)
 
 
 def test_shape_filter_identical_given_A(L):
