@@ -8,6 +8,7 @@
 #include "tc_conv.cuh"
 #include "tc_first.cuh"
 #include "tc_head.cuh"
+#include "tc_pair.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -68,6 +69,32 @@ static int launch_first2(void* out, const __half* w, const float* b, int n, int 
     return AG_OK;
 }
 
+// cta_group::2 launch: clusters of two CTAs, one patch per CTA (tc_pair.cuh)
+template <int CIN, int COUT, int H, int STRIDE, int STAGES, int OUT>
+static int launch_pair(const __half* in, void* out, const __half* w, const float* b, int n, int group, const int* count, cudaStream_t st) {
+    using Cfg = PairCfg<CIN, COUT, H, STRIDE, STAGES, OUT>;
+    auto kern = tc_conv_pair_kernel<CIN, COUT, H, STRIDE, STAGES, OUT>;
+    static bool configured = false;
+    if (!configured) {
+        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM), "tc_conv_pair smem attr");
+        if (rc != AG_OK) return rc;
+        configured = true;
+    }
+    ConvArgs a;
+    a.in = in; a.out = out; a.wpk = w; a.bias = b; a.n = n; a.group = group; a.count = count;
+    int pairs = num_sms() / 2;
+    if (pairs > (n + 1) / 2) pairs = (n + 1) / 2;
+    if (pairs < 1) pairs = 1;
+    kern<<<2 * pairs, 224, Cfg::SMEM, st>>>(a);
+    AG_CHECK_LAUNCH("tc_conv_pair_kernel");
+    return AG_OK;
+}
+
+static bool no_pair() {
+    static const bool v = getenv("AG_NO_PAIR") != nullptr;   // A/B switch: wide HardNet layers as two independent COUT halves
+    return v;
+}
+
 static bool first_simt() {
     static const bool v = getenv("AG_FIRST_SIMT") != nullptr;   // A/B switch: layer 1 on CUDA cores inside the layer-2 kernel
     return v;
@@ -118,8 +145,13 @@ int tc_hardnet_forward(const ag_net* net, const tc::FirstSrc& src0, int n, int g
     if (rc) return rc;
     if ((rc = launch_tc<32, 64, 32, 2, 1, 2, PLAIN>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
     if ((rc = launch_tc<64, 64, 16, 1, 1, 2, PHASE>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
-    if ((rc = launch_tc<64, 128, 16, 2, 2, 2, PLAIN>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
-    if ((rc = launch_tc<128, 128, 8, 1, 2, 2, HEADL>(A, headbuf, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
+    if (no_pair()) {
+        if ((rc = launch_tc<64, 128, 16, 2, 2, 2, PLAIN>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
+        if ((rc = launch_tc<128, 128, 8, 1, 2, 2, HEADL>(A, headbuf, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
+    } else {   // two SMs per MMA: every patch is read and multiplied once, each SM holds half of the weights
+        if ((rc = launch_pair<64, 128, 16, 2, 3, PLAIN>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
+        if ((rc = launch_pair<128, 128, 8, 1, 2, HEADL>(A, headbuf, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
+    }
     static bool configured = false;
     if (!configured) {
         rc = check_cuda(cudaFuncSetAttribute(tc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM), "tc_head smem attr");
