@@ -21,3 +21,9 @@ for p in "${pids[@]}"; do wait $p || fail=1; done
 if [ $fail = 1 ]; then echo "build failed" >&2; rm -f "$HERE"/obj/*.o.failed; for l in "$HERE"/obj/*.o.log; do grep -l "error" "$l" >/dev/null 2>&1 && rm -f "${l%.log}"; done; exit 1; fi
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libaffnet_b200.so" "$HERE"/obj/*.o -lcudart
 echo "built $OUT/libaffnet_b200.so"
+if [ "${AG_ROLE_PROF:-0}" = "1" ]; then mkdir -p "$HERE/obj_prof";   # developer build with the warp-role cycle counters of tc_first.cuh (scripts/role_prof.sh)
+  $NVCC $FLAGS -DAG_ROLE_PROF -c "$HERE/nets_tc.cu" -o "$HERE/obj_prof/nets_tc.o" > "$HERE/obj_prof/nets_tc.log" 2>&1 || { cat "$HERE/obj_prof/nets_tc.log"; exit 1; }
+  objs=$(ls "$HERE"/obj/*.o | grep -v nets_tc.o)
+  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libaffnet_b200_prof.so" $objs "$HERE/obj_prof/nets_tc.o" -lcudart
+  echo "built $OUT/libaffnet_b200_prof.so"
+fi

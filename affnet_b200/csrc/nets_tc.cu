@@ -206,3 +206,10 @@ int tc_nsplit(int kind, int layer) { return (kind == AG_NET_HARDNET && layer >= 
 int tc_split_w(int kind) { return kind == AG_NET_HARDNET ? 0 : 1; }
 
 }  // namespace ag
+
+#ifdef AG_ROLE_PROF
+// developer-only: per-CTA role cycle counters of the last tc_first2_kernel launch (tc_first.cuh)
+extern "C" int ag_debug_role_prof(unsigned long long* out) {
+    return cudaMemcpyFromSymbol(out, ag::tc::g_role_prof, sizeof(unsigned long long) * 160 * 20) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -31,6 +31,9 @@ struct InLay {
     static constexpr int PLANE = (STRIDE == 1) ? 0 : ((PITCH * PITCH + 7) / 8) * 8;   // parity-plane stride (slots)
     static constexpr int MAXOFF = (STRIDE == 1) ? 2 * PITCH + 2 : 3 * PLANE + PITCH + 1;
     static constexpr int NPIX = ((128 * TILES + MAXOFF + 1 + 7) / 8) * 8;     // slots per channel group incl. slack
+    // slots that hold data (padded plane / four parity planes); the slack behind them only feeds accumulator rows that are never
+    // stored, so loaders copy just this prefix of every channel group and leave whatever is in shared memory behind it
+    static constexpr int USED = (STRIDE == 1) ? (H + 2) * (H + 2) : 3 * PLANE + PITCH * PITCH;
     __host__ __device__ static constexpr int tap_off(int dy, int dx) {
         return (STRIDE == 1) ? dy * PITCH + dx : ((dy & 1) * 2 + (dx & 1)) * PLANE + (dy >> 1) * PITCH + (dx >> 1);
     }
@@ -231,9 +234,12 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
                 if (!valid(pi)) continue;
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-                mbar_expect_tx(&full[s], Cfg::IN_BYTES);
-                bulk_g2s(sIn + (size_t)s * Cfg::IN_BYTES, reinterpret_cast<const unsigned char*>(a.in) + (size_t)pi * Cfg::IN_BYTES, Cfg::IN_BYTES,
-                         &full[s]);
+                constexpr int G = KC * (1 + SA);
+                mbar_expect_tx(&full[s], (uint32_t)G * In::USED * 16u);
+                const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.in) + (size_t)pi * Cfg::IN_BYTES;
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    bulk_g2s(sIn + (size_t)s * Cfg::IN_BYTES + (size_t)g * In::NPIX * 16, gsrc + (size_t)g * In::NPIX * 16, In::USED * 16u, &full[s]);
                 it++;
             }
         }

@@ -3,10 +3,13 @@
 //   sampler (LAF.py:313-372) -> input_norm (architectures.py:231-235) -> conv3x3(1 -> C1)+BN+ReLU -> conv3x3(C1 -> COUT)+BN+ReLU
 //
 // 32x32 patches and the layer-1 activations never exist in HBM.  Layer 1 (K = 9) is made tensor-core shaped with a sliding
-// window plane: P[slot] = 8 consecutive normalised pixels (fp16), so one 16-byte core-matrix row holds the three horizontal
-// taps (elements 0..2; the weights of elements 3..7 are zero) and the vertical taps are the same plane at +pitch rows: an
-// M=128, K=16 MMA covers two tap rows through the descriptor's leading-byte offset.  Input and weights carry fp16 residual
-// planes (three MMAs per K step), so layer 1 is fp32-grade, as the accuracy budget requires (SURVEY.md §7 hard part 1).
+// window plane: P[slot] = 4 consecutive normalised pixels of the slot's row and 4 of the row below (fp16), so one 16-byte
+// core-matrix row holds two tap rows (elements 0..2 and 4..6; the weights of elements 3 and 7 are zero) and the third tap row
+// is the same plane two pitches further, reached through the descriptor's leading-byte offset: ONE M=128, K=16 MMA per tile
+// covers all nine taps (every MMA costs a 4 KB shared-memory read of its A operand, ~64 clk, whatever its N).  For the
+// input and weights carry fp16 residual planes, so layer 1 is fp32-grade, as the accuracy
+// budget requires (SURVEY.md §7 hard part 1).  (HardNet with the single hi*hi product is 6 % faster in this kernel but doubles
+// the descriptor error to 1.1e-3; it keeps the residual terms as well.)
 //
 // Warp roles (448 threads):  0 weight loader | 1 MMA issuer | 2-5 layer-2 epilogue (TMEM -> global, next layout)
 //                            6-9 layer-1 epilogue (TMEM -> bias/ReLU -> fp16 stage in shared memory) | 10-13 sampler + norm + P planes
@@ -16,29 +19,44 @@
 namespace ag {
 namespace tc {
 
+// Developer-only role profiler (build with -DAG_ROLE_PROF, scripts/role_prof.sh): cycles every warp role spends in its loop and
+// waiting on each of its barriers, per CTA.  Compiled out of the product library.
+#ifdef AG_ROLE_PROF
+__device__ unsigned long long g_role_prof[160][20];
+#define RP_DECL unsigned long long rp_t0 = clock64(), rp_w[4] = {0, 0, 0, 0}
+#define RP_WAIT(i, stmt) do { const unsigned long long rp_t = clock64(); stmt; rp_w[i] += clock64() - rp_t; } while (0)
+#define RP_STORE(role) do { if (lane == 0 && (warp == 1 || warp == 2 || warp == 6 || warp == 10)) { unsigned long long* d_ = g_role_prof[blockIdx.x] + (role) * 5; \
+    d_[0] = clock64() - rp_t0; d_[1] = rp_w[0]; d_[2] = rp_w[1]; d_[3] = rp_w[2]; d_[4] = rp_w[3]; } } while (0)
+#else
+#define RP_DECL
+#define RP_WAIT(i, stmt) stmt
+#define RP_STORE(role)
+#endif
+
 template <int C1, int COUT, int SA, int SW, int OSA>
 struct FirstCfg {
     using In = InLay<32, 1>;     // layout of the stage (input of layer 2)
     using OutS = InLay<32, 2>;   // layout of the output (input of the stride-2 layer 3)
     static constexpr int KC = C1 / 8, NT = COUT, TILES = In::TILES;
     static constexpr int NPIXP = 1280;                         // slots of a P plane: 9*128 rows + 3 pitches of look-ahead, zero tail
+    static constexpr int X1 = 1;                              // layer 1 with residual planes (x = hi + lo, w = hi + lo) for every net
     // stacked-N operands (see ConvCfg::ACCW): layer 2 when SW; layer 1 when its nine accumulators still fit TMEM (C1 = 16)
-    static constexpr int S1 = (TILES * 2 * C1 + 2 * NT * (1 + SW) <= 512) ? 1 : 0;
+    static constexpr int S1 = (X1 && TILES * 2 * C1 + 2 * NT * (1 + SW) <= 512) ? 1 : 0;
     static constexpr int ACC1 = C1 * (1 + S1);                 // layer-1 accumulator width
     static constexpr int ACCW = NT * (1 + SW);                 // layer-2 accumulator width
     static constexpr int C1COLS = TILES * ACC1;                // TMEM columns of the layer-1 accumulators (one buffer per tile)
     static constexpr int NACC = ((512 - C1COLS) / ACCW) < 8 ? ((512 - C1COLS) / ACCW) : 8;
     static constexpr uint32_t IN_BYTES = (uint32_t)KC * (1 + SA) * In::NPIX * 16;
     static constexpr uint32_t W_HALF = 9u * KC * NT * 16, W_BYTES = W_HALF * (1 + SW);
-    static constexpr uint32_t W1_HALF = 4u * C1 * 16, W1_BYTES = 2 * W1_HALF;
+    static constexpr uint32_t W1_BYTES = 2u * 2u * C1 * 16;   // [K chunk 0|1][hi rows | lo rows][8]
     static constexpr uint32_t P_BYTES = 2u * NPIXP * 16;
-    static constexpr int SX = 1296;                            // floats of one padded fp32 patch buffer (34*34 + zero tail)
+    static constexpr int SX = 1320;                            // floats of one padded fp32 patch buffer (34*34 + zero tail)
     static constexpr size_t SMEM = 1024 + (size_t)W_BYTES + 2 * (size_t)IN_BYTES + P_BYTES + W1_BYTES + 2 * SX * 4 + 256;
     static constexpr int OUT_NPIX = OutS::NPIX;
     static constexpr size_t OUT_BYTES = (size_t)(COUT / 8) * (1 + OSA) * OUT_NPIX * 16;
     static_assert(C1 % 16 == 0 && NT % 16 == 0 && NT <= 128 && NACC >= 2 && ACCW <= 256, "shape");
     static_assert(SMEM <= 232448, "shared memory budget");
-    static_assert(TILES * 128 + 3 * In::PITCH + 8 <= NPIXP, "P plane look-ahead");
+    static_assert(TILES * 128 + 2 * In::PITCH <= NPIXP && NPIXP + In::PITCH + 4 <= SX, "P plane look-ahead");
 };
 
 template <int C1, int COUT, int SA, int SW, int OSA>
@@ -62,7 +80,7 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
     unsigned char* sW = smem + 1024;
     unsigned char* sIn = sW + Cfg::W_BYTES;
     unsigned char* sP = sIn + 2 * (size_t)Cfg::IN_BYTES;    // [hi|lo][NPIXP][8] fp16
-    unsigned char* sW1 = sP + Cfg::P_BYTES;                 // [hi|lo][4][C1][8] fp16
+    unsigned char* sW1 = sP + Cfg::P_BYTES;                 // [chunk][hi|lo][C1][8] fp16
     float* s_x = reinterpret_cast<float*>(sW1 + Cfg::W1_BYTES);   // [2][SX]
     float* s_red = s_x + 2 * SX;                            // [2][4][2]
 
@@ -83,11 +101,12 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
         for (int i = 0; i < 9; i++) { mbar_init(&c1_full[i], 1); mbar_init(&c1_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 2 * 4 * C1 * 8; i += blockDim.x) {   // W1[chunk dy][hi rows | lo rows][e = dx]
-        const int e = i & 7, co = (i >> 3) % C1, part = (i / (8 * C1)) & 1, dy = i / (8 * C1 * 2);
+    for (int i = threadIdx.x; i < 2 * 2 * C1 * 8; i += blockDim.x) {   // W1[chunk][hi rows | lo rows][e]: chunk 0 = tap rows 0 (e 0..2), 1 (e 4..6); chunk 1 = tap row 2
+        const int e = i & 7, co = (i >> 3) % C1, part = (i / (8 * C1)) & 1, ch = i / (8 * C1 * 2);
+        const int dy = ch == 0 ? (e >> 2) : 2, dx = e & 3;
         float v = 0.f;
-        if (dy < 3 && e < 3) {
-            const float wv = src.w1[(dy * 3 + e) * C1 + co];
+        if (dx < 3 && (ch == 0 || e < 4)) {
+            const float wv = src.w1[(dy * 3 + dx) * C1 + co];
             const __half hi = __float2half_rn(wv);
             v = part == 0 ? __half2float(hi) : wv - __half2float(hi);
         }
@@ -120,29 +139,28 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
         const uint32_t leader = elect_one();
         mbar_wait(wbar, 0);
         tc_fence_after();
+        RP_DECL;
         const uint32_t w_lo = desc_lo(smem_u32(sW), Cfg::ACCW * 16u);
         const uint32_t w1_lo = desc_lo(smem_u32(sW1), 2 * C1 * 16u);   // K chunks are 2*C1 rows apart (hi rows, then lo rows)
-        const uint32_t p_lo = desc_lo(smem_u32(sP), In::PITCH * 16u);   // leading-byte offset = one tap row
+        const uint32_t p_lo = desc_lo(smem_u32(sP), 2 * In::PITCH * 16u);   // leading-byte offset = two tap rows
         auto issue_conv1 = [&](int n1) {
-            mbar_wait(p_full, n1 & 1);
+            RP_WAIT(0, mbar_wait(p_full, n1 & 1));
             tc_fence_after();
 #pragma unroll 1
             for (int t = 0; t < TILES; t++) {
-                mbar_wait(&c1_empty[t], (n1 & 1) ^ 1);
+                RP_WAIT(1, mbar_wait(&c1_empty[t], (n1 & 1) ^ 1));
                 tc_fence_after();
                 if (leader) {
                     const uint32_t d = tmem + (uint32_t)(t * Cfg::ACC1);
-#pragma unroll
-                    for (int j = 0; j < 2; j++) {   // tap rows (0,1) then (2, zero)
-                        const uint32_t alo = p_lo + (uint32_t)(t * 128 + 2 * j * In::PITCH);
-                        const uint32_t blo = w1_lo + (uint32_t)(2 * j * 2 * C1);
-                        if (Cfg::S1) {   // x_hi * [w_hi ; w_lo] in one MMA, then x_lo * w_hi
-                            if (j == 0) umma_f16_lo<0>(d, alo, blo, idesc1_st); else umma_f16_lo<1>(d, alo, blo, idesc1_st);
-                            umma_f16_lo<1>(d, alo + (uint32_t)NPIXP, blo, idesc1);
-                        } else {
-                            if (j == 0) umma_f16_lo<0>(d, alo, blo, idesc1); else umma_f16_lo<1>(d, alo, blo, idesc1);
-                            umma_f16_lo<1>(d, alo + (uint32_t)NPIXP, blo, idesc1);               // x_lo * w_hi
-                            umma_f16_lo<1>(d, alo, blo + (uint32_t)C1, idesc1);                   // x_hi * w_lo (lo rows follow the hi rows)
+                    const uint32_t alo = p_lo + (uint32_t)(t * 128);
+                    if (Cfg::S1) {   // x_hi * [w_hi ; w_lo] in one MMA, then x_lo * w_hi
+                        umma_f16_lo<0>(d, alo, w1_lo, idesc1_st);
+                        umma_f16_lo<1>(d, alo + (uint32_t)NPIXP, w1_lo, idesc1);
+                    } else {
+                        umma_f16_lo<0>(d, alo, w1_lo, idesc1);
+                        if (Cfg::X1) {
+                            umma_f16_lo<1>(d, alo + (uint32_t)NPIXP, w1_lo, idesc1);             // x_lo * w_hi
+                            umma_f16_lo<1>(d, alo, w1_lo + (uint32_t)C1, idesc1);                 // x_hi * w_lo (lo rows follow the hi rows)
                         }
                     }
                     umma_commit(&c1_full[t]);
@@ -155,13 +173,13 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
         int tcnt = 0;
         auto issue_l2 = [&](int it) {
             const int s = it & 1;
-            mbar_wait(&full[s], (it >> 1) & 1);
+            RP_WAIT(2, mbar_wait(&full[s], (it >> 1) & 1));
             tc_fence_after();
             const uint32_t in_lo = desc_lo(smem_u32(sIn + (size_t)s * Cfg::IN_BYTES), In::NPIX * 16u);
 #pragma unroll 1
             for (int t = 0; t < TILES; t++, tcnt++) {
                 const int ab = tcnt % NACC;
-                mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1);
+                RP_WAIT(3, mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1));
                 tc_fence_after();
                 if (leader) {
                     const uint32_t d = tmem_l2 + (uint32_t)(ab * Cfg::ACCW);
@@ -193,10 +211,12 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
             it++;
             pi = pn;
         }
+        RP_STORE(0);
     } else if (warp < 6) {
         // ===== layer-2 epilogue: TMEM -> bias + ReLU -> fp16 -> global (layout of the stride-2 consumer) =====
         const int q = warp & 3, et = (warp - 2) * 32 + lane;
         int tcnt = 0;
+        RP_DECL;
         for (int pi = next_valid(blockIdx.x); pi < a.n; pi = next_valid(pi + gridDim.x)) {
             unsigned char* outp = reinterpret_cast<unsigned char*>(a.out) + (size_t)pi * Cfg::OUT_BYTES;
             constexpr int HB = 33;
@@ -211,7 +231,7 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
 #pragma unroll 1
             for (int t = 0; t < TILES; t++, tcnt++) {
                 const int ab = tcnt % NACC;
-                mbar_wait(&tfull[ab], (tcnt / NACC) & 1);
+                RP_WAIT(0, mbar_wait(&tfull[ab], (tcnt / NACC) & 1));
                 tc_fence_after();
                 const int m = t * 128 + q * 32 + lane;
                 const int y = m / In::PITCH, x = m - y * In::PITCH;
@@ -267,17 +287,19 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
                 }
             }
         }
+        RP_STORE(1);
     } else if (warp < 10) {
         // ===== layer-1 epilogue: TMEM -> bias + ReLU -> fp16 (hi [+lo]) -> shared-memory stage of layer 2 =====
         const int q = warp & 3;
         int it = 0;
+        RP_DECL;
         for (int pi = next_valid(blockIdx.x); pi < a.n; pi = next_valid(pi + gridDim.x), it++) {
             const int s = it & 1;
-            mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+            RP_WAIT(0, mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1));
             unsigned char* st = sIn + (size_t)s * Cfg::IN_BYTES;
 #pragma unroll 1
             for (int t = 0; t < TILES; t++) {
-                mbar_wait(&c1_full[t], it & 1);
+                RP_WAIT(1, mbar_wait(&c1_full[t], it & 1));
                 tc_fence_after();
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * Cfg::ACC1);
                 uint32_t r[32];
@@ -326,6 +348,7 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&full[s]);
         }
+        RP_STORE(2);
     } else {
         // ===== producers: sampler (or patch load) -> input_norm -> sliding-window planes P_hi / P_lo =====
         const int pt = threadIdx.x - 320;   // 0..127
@@ -356,12 +379,19 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
         int pi = next_valid(blockIdx.x);
         if (pi < a.n) issue_fetch(pi);
         int it = 0;
+        RP_DECL;
         while (pi < a.n) {
             float* sx = s_x + (it & 1) * SX;
             float* red = s_red + (it & 1) * 8;
             float v[8];
+#ifdef AG_ROLE_PROF
+            const unsigned long long rp_tc = clock64();   // stalls in the combine = gather latency the prefetch did not hide
+#endif
 #pragma unroll
             for (int k = 0; k < 8; k++) v[k] = bilinear_combine(tp[k], fx[k], fy[k]);
+#ifdef AG_ROLE_PROF
+            rp_w[1] += clock64() - rp_tc + (unsigned long long)(__float_as_uint(v[0]) & 0u);
+#endif
             const int pn = next_valid(pi + gridDim.x);
             if (pn < a.n) issue_fetch(pn);
             // input_norm: mean, unbiased std + 1e-7 (two passes, as the reference)
@@ -380,27 +410,31 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
 #pragma unroll
             for (int k = 0; k < 8; k++) { const int p = pix_of(k); sx[((p >> 5) + 1) * 34 + (p & 31) + 1] = (v[k] - mean) * inv; }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            mbar_wait(p_empty, (it & 1) ^ 1);   // layer-1 MMAs of the previous patch have consumed the planes
+            RP_WAIT(0, mbar_wait(p_empty, (it & 1) ^ 1));   // layer-1 MMAs of the previous patch have consumed the planes
 #pragma unroll 1
             for (int k = 0; k < NPIXP / 128; k++) {
                 const int s0 = pt + k * 128;
                 float xv[8];
 #pragma unroll
-                for (int e = 0; e < 8; e++) xv[e] = sx[s0 + e];
-                uint4 hi, lo;
-                float r8[8];
-#pragma unroll
-                for (int e = 0; e < 8; e++) r8[e] = xv[e] - __half2float(__float2half_rn(xv[e]));
+                for (int e = 0; e < 4; e++) { xv[e] = sx[s0 + e]; xv[4 + e] = sx[s0 + In::PITCH + e]; }
+                uint4 hi;
                 hi.x = pack_h2(xv[0], xv[1]); hi.y = pack_h2(xv[2], xv[3]); hi.z = pack_h2(xv[4], xv[5]); hi.w = pack_h2(xv[6], xv[7]);
-                lo.x = pack_h2(r8[0], r8[1]); lo.y = pack_h2(r8[2], r8[3]); lo.z = pack_h2(r8[4], r8[5]); lo.w = pack_h2(r8[6], r8[7]);
                 *reinterpret_cast<uint4*>(sP + (size_t)s0 * 16) = hi;
-                *reinterpret_cast<uint4*>(sP + (size_t)(NPIXP + s0) * 16) = lo;
+                if (Cfg::X1) {
+                    uint4 lo;
+                    float r8[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) r8[e] = xv[e] - __half2float(__float2half_rn(xv[e]));
+                    lo.x = pack_h2(r8[0], r8[1]); lo.y = pack_h2(r8[2], r8[3]); lo.z = pack_h2(r8[4], r8[5]); lo.w = pack_h2(r8[6], r8[7]);
+                    *reinterpret_cast<uint4*>(sP + (size_t)(NPIXP + s0) * 16) = lo;
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(p_full);
             it++;
             pi = pn;
         }
+        RP_STORE(3);
     }
     tc_fence_before();
     __syncthreads();

@@ -126,8 +126,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1) tc_conv_pair
                 const int s = it % STAGES, pi = patch_of(pp);
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                 if (valid(pi)) {
-                    mbar_expect_tx(&full[s], Cfg::IN_BYTES);
-                    bulk_g2s(sIn + (size_t)s * Cfg::IN_BYTES, reinterpret_cast<const unsigned char*>(a.in) + (size_t)pi * Cfg::IN_BYTES, Cfg::IN_BYTES, &full[s]);
+                    mbar_expect_tx(&full[s], (uint32_t)KC * In::USED * 16u);
+                    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.in) + (size_t)pi * Cfg::IN_BYTES;
+#pragma unroll
+                    for (int g = 0; g < KC; g++)
+                        bulk_g2s(sIn + (size_t)s * Cfg::IN_BYTES + (size_t)g * In::NPIX * 16, gsrc + (size_t)g * In::NPIX * 16, In::USED * 16u, &full[s]);
                 } else {
                     mbar_arrive(&full[s]);   // nothing to load: the stage keeps stale (finite) data, its rows are never stored
                 }

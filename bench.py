@@ -332,21 +332,25 @@ def _main(real_stdout):
         step_ms = sum(sum(v) for v in per_kernel.values()) / prof_steps
         agg = sorted(((sum(v) / prof_steps, len(v) // prof_steps, k) for k, v in per_kernel.items()), reverse=True)
         pk = peaks()
-        # dominant kernel family: the tcgen05 conv trunks of the three CNNs (15 tc_conv_kernel launches per step)
+        # dominant kernel family: every tcgen05 kernel of the three CNNs (layers 1+2 fused in tc_first2_kernel, layers 3-6 in
+        # tc_conv_kernel / tc_conv_pair_kernel, HardNet's 8x8 head GEMM in tc_head_kernel); the AffNet / OriNet heads are SIMT
         n_aff, n_ori, n_hard = B * int(1.5 * K), n_desc, n_desc
-        L1F = {"aff": 2 * 16 * 9 * 1024, "hard": 2 * 32 * 9 * 1024}
-        tc_flop = (n_aff * (FLOP_PER_PATCH["affnet"] - 2 * 3 * 4096 - L1F["aff"]) + n_ori * (FLOP_PER_PATCH["orinet"] - 2 * 2 * 9 * 4096 - L1F["aff"])
-                   + n_hard * (FLOP_PER_PATCH["hardnet"] - HARD_LAYER_FLOP[6] - L1F["hard"]))
-        tc_ms = sum(t for t, n, k in agg if k == "tc_conv_kernel")
+        TC_FAMILY = ("tc_first2_kernel", "tc_conv_kernel", "tc_conv_pair_kernel", "tc_head_kernel")
+        tc_flop = (n_aff * (FLOP_PER_PATCH["affnet"] - 2 * 3 * 4096) + n_ori * (FLOP_PER_PATCH["orinet"] - 2 * 2 * 9 * 4096)
+                   + n_hard * FLOP_PER_PATCH["hardnet"])
+        tc_ms = sum(t for t, n, k in agg if k in TC_FAMILY)
+        tc_launches = sum(n for t, n, k in agg if k in TC_FAMILY)
         ach = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-        # bytes the trunks move by construction: every layer reads its input block and writes its output block once
-        roof = {"kernel": "tc_conv_kernel (15 launches/step: conv layers 2-6 of AffNet, OriNet, HardNet; tcgen05 fp16, fp32 accumulate)",
+        roof = {"kernel": "tcgen05 conv kernels (%d launches/step: tc_first2_kernel x3, tc_conv_kernel, tc_conv_pair_kernel, tc_head_kernel; fp16 operands with fp16 "
+                          "residual planes for AffNet/OriNet, fp32 accumulate in TMEM)" % tc_launches,
                 "bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"],
                 "traffic": None, "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)", "kernel_ms_per_step": tc_ms,
                 "algorithmic_flop_per_step": tc_flop, "share_of_step": tc_ms / step_ms if step_ms else None,
+                "note": "algorithmic flops = 2*MAC of the reference's fp32 convolutions; the residual-plane products (2-3 MMAs per K step for AffNet/OriNet), the "
+                        "rows of zero padding in every 128-row tile and the K=9 first layer padded to K=16 are extra tensor work that is not counted",
                 "timing": "CUDA events after every launch over %d profiled steps right after the timed region" % prof_steps,
                 "stages_ms": {k: round(t, 4) for t, n, k in agg}, "launches_ms": order}
-        cnn_ms = sum(t for t, n, k in agg if k in ("tc_conv_kernel", "first_layer_kernel", "hardnet_head_kernel", "affnet_head_kernel", "orinet_head_kernel", "conv3x3_kernel"))
+        cnn_ms = sum(t for t, n, k in agg if k in TC_FAMILY + ("first_layer_kernel", "hardnet_head_kernel", "affnet_head_kernel", "orinet_head_kernel", "conv3x3_kernel"))
         cnn_flop = n_aff * FLOP_PER_PATCH["affnet"] + n_ori * FLOP_PER_PATCH["orinet"] + n_hard * FLOP_PER_PATCH["hardnet"]
         roof["cnn_all"] = {"kernels": "all CNN kernels (first layer, tc trunks, heads)", "ms_per_step": cnn_ms, "achieved": cnn_flop / (cnn_ms * 1e-3) / 1e12 if cnn_ms else None,
                            "unit": "TFLOP/s", "algorithmic_flop_per_step": cnn_flop}

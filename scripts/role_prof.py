@@ -1,0 +1,58 @@
+"""Developer tool: where do the warp roles of tc_first2_kernel spend their cycles?
+
+    AG_ROLE_PROF=1 bash affnet_b200/csrc/build.sh
+    AFFNET_B200_LIB=affnet_b200/lib/libaffnet_b200_prof.so python scripts/role_prof.py
+
+Prints, per net, the mean over CTAs of each role's loop cycles and the cycles it spent waiting on its barriers."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+from affnet_b200.architectures import AffNetFast, OriNetFast  # noqa: E402
+from affnet_b200.HardNet import HardNet  # noqa: E402
+from affnet_b200 import _lib  # noqa: E402
+import affnet_oracle as O  # noqa: E402  (random weights only)
+
+ROLES = [("mma issuer", ["p_full", "c1_empty", "full(L1 epi done)", "tempty"]),
+         ("L2 epilogue", ["tfull", "-", "-", "-"]),
+         ("L1 epilogue", ["empty(L2 mma done)", "c1_full", "-", "-"]),
+         ("producer", ["p_empty", "gather latency", "-", "-"])]
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 32000
+    L = _lib.lib()
+    L.ag_debug_role_prof.restype = C.c_int
+    L.ag_debug_role_prof.argtypes = [C.c_void_p]
+    g = torch.Generator().manual_seed(1)
+    P = (torch.rand(n, 1, 32, 32, generator=g) * 255).cuda()
+    nets = {"affnet": AffNetFast(), "orinet": OriNetFast(PS=32), "hardnet": HardNet()}
+    for name, m in nets.items():
+        m.load_state_dict(O.random_state_dict(name, seed=3))
+        m = m.cuda().eval()
+        for _ in range(3):
+            m(P)
+        torch.cuda.synchronize()
+        launches = _lib.profile(lambda: m(P))
+        torch.cuda.synchronize()
+        buf = np.zeros((160, 20), dtype=np.uint64)
+        assert L.ag_debug_role_prof(buf.ctypes.data_as(C.c_void_p)) == 0
+        t = buf[:148].astype(np.float64)
+        per_cta = n / 148.0
+        print("== %s: %d patches, %.1f per CTA; launches: %s" % (name, n, per_cta, [(k, round(v, 3)) for k, v in launches][:2]))
+        for r, (rn, wn) in enumerate(ROLES):
+            tot = t[:, r * 5].mean()
+            line = "  %-12s total %8.0f clk/patch" % (rn, tot / per_cta)
+            for i in range(4):
+                if wn[i] != "-":
+                    line += " | wait %s %6.0f" % (wn[i], t[:, r * 5 + 1 + i].mean() / per_cta)
+            print(line)
+
+
+if __name__ == "__main__":
+    main()
