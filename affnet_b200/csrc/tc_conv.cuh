@@ -28,6 +28,12 @@ struct InLay {
     static constexpr int PITCH = (STRIDE == 1) ? H + 2 : H / 2 + 1;          // row pitch of the output-row index space
     static constexpr int ROWS = (HOUT - 1) * PITCH + HOUT;                    // output rows m = y*PITCH + x
     static constexpr int TILES = (ROWS + 127) / 128;
+    // The last tile of a multi-tile plane is issued as an M = 64 MMA when it holds at most 64 live rows: half the A-operand read,
+    // which is what bounds these MMAs.  TMEM then keeps row i of that tile in lane (i % 16) + 32 * (i / 16).
+#ifndef AG_TAIL64
+#define AG_TAIL64 1
+#endif
+    static constexpr bool TAIL64 = AG_TAIL64 && TILES > 1 && (ROWS - 128 * (TILES - 1)) <= 64;
     static constexpr int PLANE = (STRIDE == 1) ? 0 : ((PITCH * PITCH + 7) / 8) * 8;   // parity-plane stride (slots)
     static constexpr int MAXOFF = (STRIDE == 1) ? 2 * PITCH + 2 : 3 * PLANE + PITCH + 1;
     static constexpr int NPIX = ((128 * TILES + MAXOFF + 1 + 7) / 8) * 8;     // slots per channel group incl. slack
@@ -79,6 +85,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 // Descriptor-lo form: the hi word of every no-swizzle descriptor here is the constant 0x4008 (SBO = 128 B, version 1), so the
 // issuer only does one integer add per operand.  ACC is a compile-time accumulate flag.
 constexpr uint32_t DESC_HI = 0x4008u;
+constexpr uint32_t M64_FIX = (uint32_t)((128 - 64) >> 4) << 24;   // subtract from an M = 128 instruction descriptor to get M = 64
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
 template <int ACC>
 __device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc) {
@@ -266,15 +273,16 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
                 if (leader) {
                     const uint32_t d_tmem = tmem + (uint32_t)(ab * Cfg::ACCW);
                     const uint32_t a_t = in_lo + (uint32_t)(t * 128);  // 16-byte units
+                    const uint32_t mfix = (In::TAIL64 && t == TILES - 1) ? M64_FIX : 0u;   // M = 128 -> 64 in the instruction descriptor
 #pragma unroll
                     for (int tap = 0; tap < 9; tap++) {
 #pragma unroll
                         for (int j = 0; j < KC / 2; j++) {
                             const uint32_t alo = a_t + (uint32_t)(In::tap_off(tap / 3, tap % 3) + 2 * j * In::NPIX);
                             const uint32_t blo = w_lo + (uint32_t)((tap * KC + 2 * j) * Cfg::ACCW);
-                            if (tap == 0 && j == 0) umma_f16_lo<0>(d_tmem, alo, blo, idesc);                      // A_hi * [W_hi ; W_lo]
-                            else umma_f16_lo<1>(d_tmem, alo, blo, idesc);
-                            if (SA) umma_f16_lo<1>(d_tmem, alo + (uint32_t)(KC * In::NPIX), blo, idesc_hi);       // A_lo * W_hi -> hi columns
+                            if (tap == 0 && j == 0) umma_f16_lo<0>(d_tmem, alo, blo, idesc - mfix);               // A_hi * [W_hi ; W_lo]
+                            else umma_f16_lo<1>(d_tmem, alo, blo, idesc - mfix);
+                            if (SA) umma_f16_lo<1>(d_tmem, alo + (uint32_t)(KC * In::NPIX), blo, idesc_hi - mfix);   // A_lo * W_hi -> hi columns
                         }
                     }
                     umma_commit(&tfull[ab]);
@@ -435,9 +443,10 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
                 const int ab = tcnt % NACC;
                 mbar_wait(&tfull[ab], (tcnt / NACC) & 1);
                 tc_fence_after();
-                const int m = t * 128 + q * 32 + lane;
+                const bool t64 = In::TAIL64 && t == TILES - 1;
+                const int m = t * 128 + (t64 ? q * 16 : q * 32) + lane;
                 const int y = m / In::PITCH, x = m - y * In::PITCH;
-                const bool ok = (y < HOUT) && (x < HOUT);
+                const bool ok = (y < HOUT) && (x < HOUT) && !(t64 && lane >= 16);
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACCW);
 #pragma unroll
                 for (int c0 = 0; c0 < NT; c0 += 32) {

@@ -153,14 +153,15 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
                 if (leader) {
                     const uint32_t d = tmem + (uint32_t)(t * Cfg::ACC1);
                     const uint32_t alo = p_lo + (uint32_t)(t * 128);
+                    const uint32_t mfix = (In::TAIL64 && t == TILES - 1) ? M64_FIX : 0u;
                     if (Cfg::S1) {   // x_hi * [w_hi ; w_lo] in one MMA, then x_lo * w_hi
-                        umma_f16_lo<0>(d, alo, w1_lo, idesc1_st);
-                        umma_f16_lo<1>(d, alo + (uint32_t)NPIXP, w1_lo, idesc1);
+                        umma_f16_lo<0>(d, alo, w1_lo, idesc1_st - mfix);
+                        umma_f16_lo<1>(d, alo + (uint32_t)NPIXP, w1_lo, idesc1 - mfix);
                     } else {
-                        umma_f16_lo<0>(d, alo, w1_lo, idesc1);
+                        umma_f16_lo<0>(d, alo, w1_lo, idesc1 - mfix);
                         if (Cfg::X1) {
-                            umma_f16_lo<1>(d, alo + (uint32_t)NPIXP, w1_lo, idesc1);             // x_lo * w_hi
-                            umma_f16_lo<1>(d, alo, w1_lo + (uint32_t)C1, idesc1);                 // x_hi * w_lo (lo rows follow the hi rows)
+                            umma_f16_lo<1>(d, alo + (uint32_t)NPIXP, w1_lo, idesc1 - mfix);             // x_lo * w_hi
+                            umma_f16_lo<1>(d, alo, w1_lo + (uint32_t)C1, idesc1 - mfix);                 // x_hi * w_lo (lo rows follow the hi rows)
                         }
                     }
                     umma_commit(&c1_full[t]);
@@ -184,14 +185,15 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
                 if (leader) {
                     const uint32_t d = tmem_l2 + (uint32_t)(ab * Cfg::ACCW);
                     const uint32_t a_t = in_lo + (uint32_t)(t * 128);
+                    const uint32_t mfix = (In::TAIL64 && t == TILES - 1) ? M64_FIX : 0u;
 #pragma unroll
                     for (int tap = 0; tap < 9; tap++) {
 #pragma unroll
                         for (int j = 0; j < KC / 2; j++) {
                             const uint32_t alo = a_t + (uint32_t)(In::tap_off(tap / 3, tap % 3) + 2 * j * In::NPIX);
                             const uint32_t blo = w_lo + (uint32_t)((tap * KC + 2 * j) * Cfg::ACCW);
-                            if (tap == 0 && j == 0) umma_f16_lo<0>(d, alo, blo, idesc2); else umma_f16_lo<1>(d, alo, blo, idesc2);
-                            if (SA) umma_f16_lo<1>(d, alo + (uint32_t)(KC * In::NPIX), blo, idesc2_hi);
+                            if (tap == 0 && j == 0) umma_f16_lo<0>(d, alo, blo, idesc2 - mfix); else umma_f16_lo<1>(d, alo, blo, idesc2 - mfix);
+                            if (SA) umma_f16_lo<1>(d, alo + (uint32_t)(KC * In::NPIX), blo, idesc2_hi - mfix);
                         }
                     }
                     umma_commit(&tfull[ab]);
@@ -233,9 +235,10 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
                 const int ab = tcnt % NACC;
                 RP_WAIT(0, mbar_wait(&tfull[ab], (tcnt / NACC) & 1));
                 tc_fence_after();
-                const int m = t * 128 + q * 32 + lane;
+                const bool t64 = In::TAIL64 && t == TILES - 1;
+                const int m = t * 128 + (t64 ? q * 16 : q * 32) + lane;
                 const int y = m / In::PITCH, x = m - y * In::PITCH;
-                const bool ok = (y < 32) && (x < 32);
+                const bool ok = (y < 32) && (x < 32) && !(t64 && lane >= 16);
                 const uint32_t taddr = tmem_l2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACCW);
                 uint32_t r[32];
                 if (NT >= 32) {
@@ -320,9 +323,10 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&c1_empty[t]);
-                const int m = t * 128 + q * 32 + lane;
+                const bool t64 = In::TAIL64 && t == TILES - 1;
+                const int m = t * 128 + (t64 ? q * 16 : q * 32) + lane;
                 const int y = m / In::PITCH, x = m - y * In::PITCH;
-                if (y < 32 && x < 32) {
+                if (y < 32 && x < 32 && !(t64 && lane >= 16)) {
                     const int slot = In::slot(y + 1, x + 1);
 #pragma unroll
                     for (int g = 0; g < C1 / 8; g++) {
