@@ -284,6 +284,17 @@ __global__ void __launch_bounds__(256) hardnet_head_kernel(const float* __restri
 }
 
 // ---- weight packing (host) ------------------------------------------------------------------------------
+// Power of two that brings the largest |w| near 2^13.  The tensor-core engines store weights times this scale so that their
+// fp16 residuals (w - fp16(w), 2^-11 of w) stay in fp16's normal range - below 6e-5 a residual would lose bits as a subnormal -
+// and multiply the fp32 accumulators by the exact inverse.
+static float pow2_scale(const float* w, size_t n) {
+    float wmax = 0.f;
+    for (size_t i = 0; i < n; i++) wmax = fmaxf(wmax, fabsf(w[i]));
+    int ex = 0;
+    if (wmax > 0.f) { frexpf(wmax, &ex); ex = 13 - ex; }
+    return ldexpf(1.0f, ex);
+}
+
 static size_t blob_floats(int kind) {
     const LayerCfg* cfg = (kind == AG_NET_HARDNET) ? kHardCfg : kAffCfg;
     size_t n = 0;
@@ -370,10 +381,13 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
     // fp16 packs for the tensor-core engine: [nsplit][9][cin/8][hi rows | lo rows][8], layers 1..5
     std::vector<__half> packed_h;
     size_t wh_off[6] = {0, 0, 0, 0, 0, 0};
+    float w_scale[6] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    w_scale[0] = pow2_scale(packed.data() + w_off[0], (size_t)9 * cfg[0].cout);
     const int sw = tc_split_w(kind);
     for (int l = 1; l < 6; l++) {
         const int ci = cfg[l].cin, co = cfg[l].cout, ns = tc_nsplit(kind, l), nt = co / ns, kc = ci / 8;
         const float* wf = packed.data() + w_off[l];  // [tap][ci][co]
+        w_scale[l] = pow2_scale(wf, (size_t)9 * ci * co);
         wh_off[l] = packed_h.size();
         packed_h.resize(packed_h.size() + (size_t)9 * ci * co * (1 + sw));
         __half* dst = packed_h.data() + wh_off[l];
@@ -383,7 +397,7 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
                     for (int part = 0; part <= sw; part++)
                         for (int nn = 0; nn < nt; nn++)
                             for (int e = 0; e < 8; e++) {
-                                const float v = wf[((size_t)tap * ci + g * 8 + e) * co + sp * nt + nn];
+                                const float v = w_scale[l] * wf[((size_t)tap * ci + g * 8 + e) * co + sp * nt + nn];
                                 const __half hi = __float2half_rn(v);
                                 const __half val = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
                                 // [nsplit][9][kc][hi rows | lo rows][8]
@@ -391,6 +405,7 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
                             }
     }
     size_t headh_off = 0;
+    float head_scale = 1.0f;
     if (kind == AG_NET_HARDNET) {
         while (packed_h.size() % 8) packed_h.push_back(__float2half_rn(0.f));
         headh_off = packed_h.size();
@@ -403,17 +418,41 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
                     for (int e = 0; e < 8; e++)
                         dst[(((size_t)(pix * 16 + cg)) * 128 + o) * 8 + e] = __float2half_rn(hw[((size_t)(cg * 8 + e) * 64 + pix) * 128 + o]);
     }
+    if (kind != AG_NET_HARDNET) {   // AffNet (3 outputs) / OriNet (18 shifted outputs): [4096/8][32 hi rows | 32 lo rows][8]
+        const int no = (kind == AG_NET_AFFNET) ? 3 : 18;
+        while (packed_h.size() % 8) packed_h.push_back(__float2half_rn(0.f));
+        headh_off = packed_h.size();
+        packed_h.resize(packed_h.size() + (size_t)4096 * 64, __float2half_rn(0.f));
+        __half* dst = packed_h.data() + headh_off;
+        const float* hw = packed.data() + hw_off;
+        // the weights are stored times a power of two that brings the largest one near 2^13: their fp16 residuals then stay in
+        // the normal range (a residual below 6e-5 would lose bits as a subnormal); the epilogue multiplies by 1/scale, exactly
+        head_scale = pow2_scale(hw, (size_t)4096 * no);
+        for (int pix = 0; pix < 64; pix++)
+            for (int cg = 0; cg < 8; cg++)
+                for (int o = 0; o < no; o++)
+                    for (int e = 0; e < 8; e++) {
+                        const size_t k = (size_t)(cg * 8 + e) * 64 + pix;
+                        const float v = head_scale * ((kind == AG_NET_AFFNET) ? hw[(size_t)o * 4096 + k] : hw[k * 18 + o]);
+                        const __half hi = __float2half_rn(v);
+                        const size_t chunk = (size_t)pix * 8 + cg;
+                        dst[(chunk * 64 + o) * 8 + e] = hi;
+                        dst[(chunk * 64 + 32 + o) * 8 + e] = __float2half_rn(v - __half2float(hi));
+                    }
+    }
     ag_net* net = new ag_net();
     memset(net, 0, sizeof(*net));
     net->kind = kind;
     net->engine = AG_ENGINE_TC;
+    net->head_inv_scale = 1.0f / head_scale;
+    for (int l = 0; l < 6; l++) net->w_inv_scale[l] = 1.0f / w_scale[l];
     {
         int rch = check_cuda(cudaMalloc(&net->d_all_h, packed_h.size() * sizeof(__half)), "cudaMalloc fp16 weights");
         if (rch != AG_OK) { delete net; return rch; }
         rch = check_cuda(cudaMemcpy(net->d_all_h, packed_h.data(), packed_h.size() * sizeof(__half), cudaMemcpyHostToDevice), "upload fp16 weights");
         if (rch != AG_OK) { cudaFree(net->d_all_h); delete net; return rch; }
         for (int l = 1; l < 6; l++) net->d_wh[l] = net->d_all_h + wh_off[l];
-        if (kind == AG_NET_HARDNET) net->d_headh = net->d_all_h + headh_off;
+        net->d_headh = net->d_all_h + headh_off;
     }
     int rc = check_cuda(cudaMalloc(&net->d_all, packed.size() * sizeof(float)), "cudaMalloc weights");
     if (rc != AG_OK) { cudaFree(net->d_all_h); delete net; return rc; }
@@ -448,10 +487,10 @@ size_t ag_net_workspace_bytes(int kind, int n) {
     if (n <= 0) return 0;
     const size_t per = (kind == AG_NET_HARDNET) ? 32768 : 16384;  // largest fp32 activation per patch (floats), SIMT engine
     const size_t simt = 2 * align_up((size_t)n * per * sizeof(float), 256);
-    // tensor-core engine: two fp16 ping-pong buffers + fp32 features (AffNet/OriNet) or the fp16 head operand (HardNet, padded
+    // tensor-core engine: two fp16 ping-pong buffers + the hi/lo fp16 head operand (AffNet/OriNet, whole 128-patch tiles) or the fp16 head operand (HardNet, padded
     // to a multiple of 128 patches)
     const size_t tcb = 2 * align_up((size_t)n * tc_act_bytes(kind == AG_NET_AFFNET ? AG_NET_ORINET : kind), 256) +
-                       (kind == AG_NET_HARDNET ? align_up(((size_t)n + 128) * 8192 * 2, 256) : align_up((size_t)n * 64 * 64 * sizeof(float), 256));
+                       (kind == AG_NET_HARDNET ? align_up(((size_t)n + 128) * 8192 * 2, 256) : align_up(tc_headx_bytes(n), 256));
     return simt > tcb ? simt : tcb;
 }
 
@@ -483,16 +522,17 @@ static int trunk_hardnet(const ag_net* net, const float* patches, int n, int gro
     return AG_OK;  // features in b: [n,128,8,8]
 }
 
-// Runs the six conv layers with the net's engine; *feat receives the fp32 NCHW feature pointer ([n,C,8,8]).
+// Runs the six conv layers with the net's engine; *feat receives the feature pointer: fp32 NCHW [n,C,8,8] (SIMT engine) or the
+// fp16 hi/lo head-GEMM operand (tensor-core engines).
 static int run_trunk(const ag_net* net, const float* patches, const tc::FirstSrc* pyr_src, int n, int group, const int* count, float* a,
                      float* b, float** feat, cudaStream_t st) {
     if (net->engine != AG_ENGINE_SIMT) {
         const tc::FirstSrc src = pyr_src ? *pyr_src : tc_src_patches(patches);
-        // the workspace [a, a + 2*(b-a)) is re-carved as [bufA | bufB | fp32 features]
+        // the workspace [a, a + 2*(b-a)) is re-carved as [bufA | bufB | head-GEMM operand]
         char* base = (char*)a;
         const size_t total = 2 * (size_t)((char*)b - (char*)a);
         const size_t act = align_up((size_t)n * tc_act_bytes(net->engine == AG_ENGINE_TC_EXACT ? AG_NET_ORINET : net->kind), 256);
-        const size_t fbytes = (size_t)n * 64 * 64 * sizeof(float);
+        const size_t fbytes = tc_headx_bytes(n);
         if (2 * act + fbytes > total) { set_error("tensor-core workspace too small"); return AG_ERR_CAPACITY; }
         void* bufA = base;
         void* bufB = base + act;
@@ -534,6 +574,7 @@ static int affnet_impl(const ag_net_t* net, const float* d_patches, const tc::Fi
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = run_trunk(net, d_patches, src, n, group, d_count, a, b, &b, st))) return rc;
+    if (net->engine == AG_ENGINE_TC) return tc_headx_forward(net, b, n, group, d_count, d_out, nullptr, st);
     affnet_head_kernel<<<cdiv(n, 8), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, n, group, d_count);
     AG_CHECK_LAUNCH("affnet_head_kernel");
     return AG_OK;
@@ -550,6 +591,7 @@ static int orinet_impl(const ag_net_t* net, const float* d_patches, const tc::Fi
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = run_trunk(net, d_patches, src, n, group, d_count, a, b, &b, st))) return rc;
+    if (net->engine == AG_ENGINE_TC) return tc_headx_forward(net, b, n, group, d_count, d_out, d_angle, st);
     orinet_head_kernel<<<cdiv(n, OH_W * OH_P), OH_W * 32, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, d_angle, n, group, d_count);
     AG_CHECK_LAUNCH("orinet_head_kernel");
     return AG_OK;

@@ -27,7 +27,7 @@ static int num_sms() {
 }
 
 template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA = 0, int SW = 0, int OSA = 0, int FIRST = 0>
-static int launch_tc(const __half* in, void* out, const __half* w, const float* b, int n, int group, const int* count, cudaStream_t st,
+static int launch_tc(const __half* in, void* out, const __half* w, const float* b, float inv_scale, int n, int group, const int* count, cudaStream_t st,
                      const FirstSrc* src = nullptr) {
     using Cfg = ConvCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, FIRST>;
     auto kern = tc_conv_kernel<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, FIRST>;
@@ -38,7 +38,7 @@ static int launch_tc(const __half* in, void* out, const __half* w, const float* 
         configured = true;
     }
     ConvArgs a;
-    a.in = in; a.out = out; a.wpk = w; a.bias = b; a.n = n; a.group = group; a.count = count;
+    a.in = in; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.n = n; a.group = group; a.count = count;
     int gx = num_sms() / NSPLIT;
     if (gx > n) gx = n;
     if (gx < 1) gx = 1;
@@ -50,7 +50,7 @@ static int launch_tc(const __half* in, void* out, const __half* w, const float* 
 }
 
 template <int C1, int COUT, int SA, int SW, int OSA>
-static int launch_first2(void* out, const __half* w, const float* b, int n, int group, const int* count, cudaStream_t st, const FirstSrc& src) {
+static int launch_first2(void* out, const __half* w, const float* b, float inv_scale, int n, int group, const int* count, cudaStream_t st, const FirstSrc& src) {
     using Cfg = FirstCfg<C1, COUT, SA, SW, OSA>;
     auto kern = tc_first2_kernel<C1, COUT, SA, SW, OSA>;
     static bool configured = false;
@@ -60,7 +60,7 @@ static int launch_first2(void* out, const __half* w, const float* b, int n, int 
         configured = true;
     }
     ConvArgs a;
-    a.in = nullptr; a.out = out; a.wpk = w; a.bias = b; a.n = n; a.group = group; a.count = count;
+    a.in = nullptr; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.n = n; a.group = group; a.count = count;
     int gx = num_sms();
     if (gx > n) gx = n;
     if (gx < 1) gx = 1;
@@ -71,7 +71,7 @@ static int launch_first2(void* out, const __half* w, const float* b, int n, int 
 
 // cta_group::2 launch: clusters of two CTAs, one patch per CTA (tc_pair.cuh)
 template <int CIN, int COUT, int H, int STRIDE, int STAGES, int OUT>
-static int launch_pair(const __half* in, void* out, const __half* w, const float* b, int n, int group, const int* count, cudaStream_t st) {
+static int launch_pair(const __half* in, void* out, const __half* w, const float* b, float inv_scale, int n, int group, const int* count, cudaStream_t st) {
     using Cfg = PairCfg<CIN, COUT, H, STRIDE, STAGES, OUT>;
     auto kern = tc_conv_pair_kernel<CIN, COUT, H, STRIDE, STAGES, OUT>;
     static bool configured = false;
@@ -81,7 +81,7 @@ static int launch_pair(const __half* in, void* out, const __half* w, const float
         configured = true;
     }
     ConvArgs a;
-    a.in = in; a.out = out; a.wpk = w; a.bias = b; a.n = n; a.group = group; a.count = count;
+    a.in = in; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.n = n; a.group = group; a.count = count;
     int pairs = num_sms() / 2;
     if (pairs > (n + 1) / 2) pairs = (n + 1) / 2;
     if (pairs < 1) pairs = 1;
@@ -138,19 +138,19 @@ int tc_hardnet_forward(const ag_net* net, const tc::FirstSrc& src0, int n, int g
     __half* A = (__half*)bufA;
     __half* B = (__half*)bufB;
     FirstSrc src = src0;
-    src.w1 = net->d_w1; src.b1 = net->d_b[0];
+    src.w1 = net->d_w1; src.b1 = net->d_b[0]; src.w1_inv = net->w_inv_scale[0]; src.w1_scale = 1.0f / net->w_inv_scale[0];
     int rc;
-    if (first_simt()) rc = launch_tc<32, 32, 32, 1, 1, 2, PHASE, 0, 0, 0, 1>(nullptr, B, net->d_wh[1], net->d_b[1], n, group, count, st, &src);
-    else rc = launch_first2<32, 32, 0, 0, 0>(B, net->d_wh[1], net->d_b[1], n, group, count, st, src);
+    if (first_simt()) rc = launch_tc<32, 32, 32, 1, 1, 2, PHASE, 0, 0, 0, 1>(nullptr, B, net->d_wh[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, &src);
+    else rc = launch_first2<32, 32, 0, 0, 0>(B, net->d_wh[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src);
     if (rc) return rc;
-    if ((rc = launch_tc<32, 64, 32, 2, 1, 2, PLAIN>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
-    if ((rc = launch_tc<64, 64, 16, 1, 1, 2, PHASE>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
+    if ((rc = launch_tc<32, 64, 32, 2, 1, 2, PLAIN>(B, A, net->d_wh[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
+    if ((rc = launch_tc<64, 64, 16, 1, 1, 2, PHASE>(A, B, net->d_wh[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
     if (no_pair()) {
-        if ((rc = launch_tc<64, 128, 16, 2, 2, 2, PLAIN>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
-        if ((rc = launch_tc<128, 128, 8, 1, 2, 2, HEADL>(A, headbuf, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
+        if ((rc = launch_tc<64, 128, 16, 2, 2, 2, PLAIN>(B, A, net->d_wh[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
+        if ((rc = launch_tc<128, 128, 8, 1, 2, 2, HEADL>(A, headbuf, net->d_wh[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st))) return rc;
     } else {   // two SMs per MMA: every patch is read and multiplied once, each SM holds half of the weights
-        if ((rc = launch_pair<64, 128, 16, 2, 3, PLAIN>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
-        if ((rc = launch_pair<128, 128, 8, 1, 2, HEADL>(A, headbuf, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
+        if ((rc = launch_pair<64, 128, 16, 2, 3, PLAIN>(B, A, net->d_wh[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
+        if ((rc = launch_pair<128, 128, 8, 1, 2, HEADL>(A, headbuf, net->d_wh[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st))) return rc;
     }
     static bool configured = false;
     if (!configured) {
@@ -163,44 +163,65 @@ int tc_hardnet_forward(const ag_net* net, const tc::FirstSrc& src0, int n, int g
     return AG_OK;
 }
 
-// AffNet trunk -> fp32 features [n,64,8,8].  Weights split hi/lo (A error 1.8e-4; plain fp16 weights give 1.8e-3).
-int tc_trunk_affnet(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
+// AffNet trunk -> features as fp16 hi + lo planes in the head-GEMM layout (tc_head.cuh).  Weights split hi/lo (A error 1.8e-4; plain fp16 weights give 1.8e-3).
+int tc_trunk_affnet(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, void* feat,
                     cudaStream_t st) {
     using namespace tc;
     __half* A = (__half*)bufA;
     __half* B = (__half*)bufB;
     FirstSrc src = src0;
-    src.w1 = net->d_w1; src.b1 = net->d_b[0];
+    src.w1 = net->d_w1; src.b1 = net->d_b[0]; src.w1_inv = net->w_inv_scale[0]; src.w1_scale = 1.0f / net->w_inv_scale[0];
     int rc;
-    if (first_simt()) rc = launch_tc<16, 16, 32, 1, 1, 2, PHASE, 0, 1, 0, 1>(nullptr, B, net->d_wh[1], net->d_b[1], n, group, count, st, &src);
-    else rc = launch_first2<16, 16, 0, 1, 0>(B, net->d_wh[1], net->d_b[1], n, group, count, st, src);
+    if (first_simt()) rc = launch_tc<16, 16, 32, 1, 1, 2, PHASE, 0, 1, 0, 1>(nullptr, B, net->d_wh[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, &src);
+    else rc = launch_first2<16, 16, 0, 1, 0>(B, net->d_wh[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src);
     if (rc) return rc;
-    if ((rc = launch_tc<16, 32, 32, 2, 1, 4, PLAIN, 0, 1, 0>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
-    if ((rc = launch_tc<32, 32, 16, 1, 1, 6, PHASE, 0, 1, 0>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
-    if ((rc = launch_tc<32, 64, 16, 2, 1, 5, PLAIN, 0, 1, 0>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
-    if ((rc = launch_tc<64, 64, 8, 1, 1, 4, FINAL, 0, 1, 0>(A, feat, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
+    if ((rc = launch_tc<16, 32, 32, 2, 1, 4, PLAIN, 0, 1, 0>(B, A, net->d_wh[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
+    if ((rc = launch_tc<32, 32, 16, 1, 1, 6, PHASE, 0, 1, 0>(A, B, net->d_wh[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
+    if ((rc = launch_tc<32, 64, 16, 2, 1, 5, PLAIN, 0, 1, 0>(B, A, net->d_wh[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
+    if ((rc = launch_tc<64, 64, 8, 1, 1, 4, HEADL, 0, 1, 1>(A, feat, net->d_wh[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st))) return rc;
     return AG_OK;
 }
 
-// OriNet trunk -> fp32 features [n,64,8,8].  The angle is ill-conditioned in the features (fp16 activations give 8e-3 rad),
+// OriNet trunk (and AffNet under the exact engine) -> features as fp16 hi + lo planes in the head-GEMM layout, or fp32 [n,64,8,8].  The angle is ill-conditioned in the features (fp16 activations give 8e-3 rad),
 // so both operands are split: three MMAs per K step, fp32-grade result (1.6e-5 rad in emulation).
-int tc_trunk_orinet(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, float* feat,
+int tc_trunk_orinet(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, void* feat,
                     cudaStream_t st) {
     using namespace tc;
     __half* A = (__half*)bufA;
     __half* B = (__half*)bufB;
     FirstSrc src = src0;
-    src.w1 = net->d_w1; src.b1 = net->d_b[0];
+    src.w1 = net->d_w1; src.b1 = net->d_b[0]; src.w1_inv = net->w_inv_scale[0]; src.w1_scale = 1.0f / net->w_inv_scale[0];
     int rc;
-    if (first_simt()) rc = launch_tc<16, 16, 32, 1, 1, 2, PHASE, 1, 1, 1, 1>(nullptr, B, net->d_wh[1], net->d_b[1], n, group, count, st, &src);
-    else rc = launch_first2<16, 16, 1, 1, 1>(B, net->d_wh[1], net->d_b[1], n, group, count, st, src);
+    if (first_simt()) rc = launch_tc<16, 16, 32, 1, 1, 2, PHASE, 1, 1, 1, 1>(nullptr, B, net->d_wh[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, &src);
+    else rc = launch_first2<16, 16, 1, 1, 1>(B, net->d_wh[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src);
     if (rc) return rc;
-    if ((rc = launch_tc<16, 32, 32, 2, 1, 2, PLAIN, 1, 1, 1>(B, A, net->d_wh[2], net->d_b[2], n, group, count, st))) return rc;
-    if ((rc = launch_tc<32, 32, 16, 1, 1, 3, PHASE, 1, 1, 1>(A, B, net->d_wh[3], net->d_b[3], n, group, count, st))) return rc;
-    if ((rc = launch_tc<32, 64, 16, 2, 1, 2, PLAIN, 1, 1, 1>(B, A, net->d_wh[4], net->d_b[4], n, group, count, st))) return rc;
-    if ((rc = launch_tc<64, 64, 8, 1, 1, 2, FINAL, 1, 1, 0>(A, feat, net->d_wh[5], net->d_b[5], n, group, count, st))) return rc;
+    if ((rc = launch_tc<16, 32, 32, 2, 1, 2, PLAIN, 1, 1, 1>(B, A, net->d_wh[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
+    if ((rc = launch_tc<32, 32, 16, 1, 1, 3, PHASE, 1, 1, 1>(A, B, net->d_wh[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
+    if ((rc = launch_tc<32, 64, 16, 2, 1, 2, PLAIN, 1, 1, 1>(B, A, net->d_wh[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
+    // default engine: hi/lo head-GEMM operand; exact engine: fp32 NCHW features for the fp32 FMA-chain heads of nets_simt.cu
+    if (net->engine == AG_ENGINE_TC_EXACT) return launch_tc<64, 64, 8, 1, 1, 2, FINAL, 1, 1, 0>(A, feat, net->d_wh[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st);
+    return launch_tc<64, 64, 8, 1, 1, 2, HEADL, 1, 1, 1>(A, feat, net->d_wh[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st);
+}
+
+// AffNet / OriNet head on tensor cores over the hi/lo feature planes the trunks above leave in `feat`
+int tc_headx_forward(const ag_net* net, const void* feat, int n, int group, const int* count, float* out, float* angle, cudaStream_t st) {
+    using namespace tc;
+    static bool configured = false;
+    if (!configured) {
+        int rc = check_cuda(cudaFuncSetAttribute(tc_headx_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HX_SMEM), "tc_headx smem attr");
+        if (rc == AG_OK) rc = check_cuda(cudaFuncSetAttribute(tc_headx_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HX_SMEM), "tc_headx smem attr");
+        if (rc != AG_OK) return rc;
+        configured = true;
+    }
+    const int tiles = (n + 127) / 128;
+    if (net->kind == AG_NET_AFFNET) tc_headx_kernel<0><<<tiles, 192, HX_SMEM, st>>>((const __half*)feat, net->d_headh, net->d_head_b, net->head_inv_scale, out, nullptr, n, group, count);
+    else tc_headx_kernel<1><<<tiles, 192, HX_SMEM, st>>>((const __half*)feat, net->d_headh, net->d_head_b, net->head_inv_scale, out, angle, n, group, count);
+    AG_CHECK_LAUNCH("tc_headx_kernel");
     return AG_OK;
 }
+
+// bytes of the head-GEMM operand of n patches (hi + lo planes, padded to whole 128-patch tiles)
+size_t tc_headx_bytes(int n) { return (size_t)((n + 127) / 128) * 2 * tc::HX_PLANE_TILE; }
 
 int tc_nsplit(int kind, int layer) { return (kind == AG_NET_HARDNET && layer >= 4) ? 2 : 1; }
 int tc_split_w(int kind) { return kind == AG_NET_HARDNET ? 0 : 1; }

@@ -146,6 +146,7 @@ struct FirstSrc {
     const int* lvl;
     int cap;
     const float* w1;        // [9][C1] fp32 (BatchNorm folded)
+    float w1_scale, w1_inv; // tensor-core layer 1: weights are used times w1_scale (a power of two), accumulators times w1_inv
     const float* b1;        // [C1]
     PyrGeomTC geom;
 };
@@ -155,6 +156,7 @@ struct ConvArgs {
     void* out;            // next layer's canonical fp16 buffer, or fp32 [n][COUT][HOUT][HOUT]
     const __half* wpk;    // [NSPLIT][9][CIN/8][hi rows | lo rows][8]: (1+SW)*COUT/NSPLIT rows per K chunk
     const float* bias;    // [COUT]
+    float inv_scale;      // wpk holds the weights times a power of two (fp16 residuals stay normal); accumulators are multiplied by its inverse
     int n, group;
     const int* count;
 };
@@ -485,10 +487,10 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
                             const int ch = split * NT + c0 + g * 8;
                             float v[8];
                             const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8 + 4);
-                            v[0] = fmaxf(__uint_as_float(r[g * 8 + 0]) + b0.x, 0.f); v[1] = fmaxf(__uint_as_float(r[g * 8 + 1]) + b0.y, 0.f);
-                            v[2] = fmaxf(__uint_as_float(r[g * 8 + 2]) + b0.z, 0.f); v[3] = fmaxf(__uint_as_float(r[g * 8 + 3]) + b0.w, 0.f);
-                            v[4] = fmaxf(__uint_as_float(r[g * 8 + 4]) + b1.x, 0.f); v[5] = fmaxf(__uint_as_float(r[g * 8 + 5]) + b1.y, 0.f);
-                            v[6] = fmaxf(__uint_as_float(r[g * 8 + 6]) + b1.z, 0.f); v[7] = fmaxf(__uint_as_float(r[g * 8 + 7]) + b1.w, 0.f);
+                            v[0] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 0]), a.inv_scale, b0.x), 0.f); v[1] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 1]), a.inv_scale, b0.y), 0.f);
+                            v[2] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 2]), a.inv_scale, b0.z), 0.f); v[3] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 3]), a.inv_scale, b0.w), 0.f);
+                            v[4] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 4]), a.inv_scale, b1.x), 0.f); v[5] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 5]), a.inv_scale, b1.y), 0.f);
+                            v[6] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 6]), a.inv_scale, b1.z), 0.f); v[7] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 7]), a.inv_scale, b1.w), 0.f);
                             if (OUT == FINAL) {
                                 float* o = reinterpret_cast<float*>(outp);
 #pragma unroll
@@ -498,7 +500,15 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
                                 pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
                                 const size_t kch = (size_t)(y * HOUT + x) * (COUT / 8) + ch / 8;
                                 unsigned char* hb = reinterpret_cast<unsigned char*>(a.out);
-                                *reinterpret_cast<uint4*>(hb + (((size_t)(pi >> 7) * (HOUT * HOUT * COUT / 8) + kch) * 128 + (pi & 127)) * 16) = pk;
+                                const size_t off = (((size_t)(pi >> 7) * (HOUT * HOUT * COUT / 8) + kch) * 128 + (pi & 127)) * 16;
+                                *reinterpret_cast<uint4*>(hb + off) = pk;
+                                if (OSA) {   // residual plane behind the hi plane of all ceil(n/128) tiles
+                                    float l[8];
+#pragma unroll
+                                    for (int e = 0; e < 8; e++) l[e] = v[e] - __half2float(__float2half_rn(v[e]));
+                                    pk.x = pack_h2(l[0], l[1]); pk.y = pack_h2(l[2], l[3]); pk.z = pack_h2(l[4], l[5]); pk.w = pack_h2(l[6], l[7]);
+                                    *reinterpret_cast<uint4*>(hb + (size_t)((a.n + 127) >> 7) * (HOUT * HOUT * COUT / 8) * 128 * 16 + off) = pk;
+                                }
                             } else {
                                 const int slot = (OUT == PLAIN) ? Cfg::OutP::slot(y + 1, x + 1) : Cfg::OutS::slot(y + 1, x + 1);
                                 uint4 pk;

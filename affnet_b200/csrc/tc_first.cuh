@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
         const int dy = ch == 0 ? (e >> 2) : 2, dx = e & 3;
         float v = 0.f;
         if (dx < 3 && (ch == 0 || e < 4)) {
-            const float wv = src.w1[(dy * 3 + dx) * C1 + co];
+            const float wv = src.w1[(dy * 3 + dx) * C1 + co] * src.w1_scale;   // power-of-two scale, undone in the epilogue
             const __half hi = __float2half_rn(wv);
             v = part == 0 ? __half2float(hi) : wv - __half2float(hi);
         }
@@ -272,10 +272,10 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
                     for (int g = 0; g < NT / 8; g++) {
                         float v[8];
                         const float4 b0 = *reinterpret_cast<const float4*>(s_bias + g * 8), b1 = *reinterpret_cast<const float4*>(s_bias + g * 8 + 4);
-                        v[0] = fmaxf(__uint_as_float(r[g * 8 + 0]) + b0.x, 0.f); v[1] = fmaxf(__uint_as_float(r[g * 8 + 1]) + b0.y, 0.f);
-                        v[2] = fmaxf(__uint_as_float(r[g * 8 + 2]) + b0.z, 0.f); v[3] = fmaxf(__uint_as_float(r[g * 8 + 3]) + b0.w, 0.f);
-                        v[4] = fmaxf(__uint_as_float(r[g * 8 + 4]) + b1.x, 0.f); v[5] = fmaxf(__uint_as_float(r[g * 8 + 5]) + b1.y, 0.f);
-                        v[6] = fmaxf(__uint_as_float(r[g * 8 + 6]) + b1.z, 0.f); v[7] = fmaxf(__uint_as_float(r[g * 8 + 7]) + b1.w, 0.f);
+                        v[0] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 0]), a.inv_scale, b0.x), 0.f); v[1] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 1]), a.inv_scale, b0.y), 0.f);
+                        v[2] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 2]), a.inv_scale, b0.z), 0.f); v[3] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 3]), a.inv_scale, b0.w), 0.f);
+                        v[4] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 4]), a.inv_scale, b1.x), 0.f); v[5] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 5]), a.inv_scale, b1.y), 0.f);
+                        v[6] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 6]), a.inv_scale, b1.z), 0.f); v[7] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 7]), a.inv_scale, b1.w), 0.f);
                         uint4 pk;
                         pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
                         *reinterpret_cast<uint4*>(outp + ((size_t)g * Cfg::OUT_NPIX + slot) * 16) = pk;
@@ -332,10 +332,10 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
                     for (int g = 0; g < C1 / 8; g++) {
                         float v[8];
                         const float4 b0 = *reinterpret_cast<const float4*>(s_bias1 + g * 8), b1 = *reinterpret_cast<const float4*>(s_bias1 + g * 8 + 4);
-                        v[0] = fmaxf(__uint_as_float(r[g * 8 + 0]) + b0.x, 0.f); v[1] = fmaxf(__uint_as_float(r[g * 8 + 1]) + b0.y, 0.f);
-                        v[2] = fmaxf(__uint_as_float(r[g * 8 + 2]) + b0.z, 0.f); v[3] = fmaxf(__uint_as_float(r[g * 8 + 3]) + b0.w, 0.f);
-                        v[4] = fmaxf(__uint_as_float(r[g * 8 + 4]) + b1.x, 0.f); v[5] = fmaxf(__uint_as_float(r[g * 8 + 5]) + b1.y, 0.f);
-                        v[6] = fmaxf(__uint_as_float(r[g * 8 + 6]) + b1.z, 0.f); v[7] = fmaxf(__uint_as_float(r[g * 8 + 7]) + b1.w, 0.f);
+                        v[0] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 0]), src.w1_inv, b0.x), 0.f); v[1] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 1]), src.w1_inv, b0.y), 0.f);
+                        v[2] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 2]), src.w1_inv, b0.z), 0.f); v[3] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 3]), src.w1_inv, b0.w), 0.f);
+                        v[4] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 4]), src.w1_inv, b1.x), 0.f); v[5] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 5]), src.w1_inv, b1.y), 0.f);
+                        v[6] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 6]), src.w1_inv, b1.z), 0.f); v[7] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 7]), src.w1_inv, b1.w), 0.f);
                         uint4 pk;
                         pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
                         *reinterpret_cast<uint4*>(st + ((size_t)g * In::NPIX + slot) * 16) = pk;

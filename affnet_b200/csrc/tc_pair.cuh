@@ -225,10 +225,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1) tc_conv_pair
                         const int ch = c0 + g * 8;
                         float v[8];
                         const float4 b0 = *reinterpret_cast<const float4*>(s_bias + ch), b1 = *reinterpret_cast<const float4*>(s_bias + ch + 4);
-                        v[0] = fmaxf(__uint_as_float(r[g * 8 + 0]) + b0.x, 0.f); v[1] = fmaxf(__uint_as_float(r[g * 8 + 1]) + b0.y, 0.f);
-                        v[2] = fmaxf(__uint_as_float(r[g * 8 + 2]) + b0.z, 0.f); v[3] = fmaxf(__uint_as_float(r[g * 8 + 3]) + b0.w, 0.f);
-                        v[4] = fmaxf(__uint_as_float(r[g * 8 + 4]) + b1.x, 0.f); v[5] = fmaxf(__uint_as_float(r[g * 8 + 5]) + b1.y, 0.f);
-                        v[6] = fmaxf(__uint_as_float(r[g * 8 + 6]) + b1.z, 0.f); v[7] = fmaxf(__uint_as_float(r[g * 8 + 7]) + b1.w, 0.f);
+                        v[0] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 0]), a.inv_scale, b0.x), 0.f); v[1] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 1]), a.inv_scale, b0.y), 0.f);
+                        v[2] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 2]), a.inv_scale, b0.z), 0.f); v[3] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 3]), a.inv_scale, b0.w), 0.f);
+                        v[4] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 4]), a.inv_scale, b1.x), 0.f); v[5] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 5]), a.inv_scale, b1.y), 0.f);
+                        v[6] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 6]), a.inv_scale, b1.z), 0.f); v[7] = fmaxf(fmaf(__uint_as_float(r[g * 8 + 7]), a.inv_scale, b1.w), 0.f);
                         if (OUT == FINAL) {
                             float* o = reinterpret_cast<float*>(outp);
 #pragma unroll

@@ -236,10 +236,13 @@ def test_nets_vs_oracle(L, nets, engine):
             aff.set_engine(L.ENGINE_TC_EXACT)
             P = sets[0]
             dA = (aff(P.to(DEV)).cpu() - O.affnet_forward(P, W["affnet"])).abs().max().item()
-            print("engine tc-exact: max|dA| %.2e" % dA)
-            assert dA < 2e-5
+            ori.set_engine(L.ENGINE_TC_EXACT)
+            dang = ori(P.to(DEV), return_rot_matrix=False).cpu() - O.orinet_angle(P, W["orinet"])
+            dang = torch.atan2(torch.sin(dang), torch.cos(dang)).abs().max().item()
+            print("engine tc-exact: max|dA| %.2e  max|dangle| %.2e rad" % (dA, dang))
+            assert dA < 2e-5 and dang < 1e-4
         finally:
-            aff.set_engine(L.ENGINE_TC)
+            aff.set_engine(L.ENGINE_TC); ori.set_engine(L.ENGINE_TC)
 
 
 def test_shape_filter_identical_given_A(L):
