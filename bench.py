@@ -31,6 +31,19 @@ FLOP_PER_PATCH = {"affnet": 19.19e6, "orinet": 19.32e6, "hardnet": 78.18e6}   # 
 HARD_LAYER_FLOP = [2 * 294912, 2 * 9437184, 2 * 4718592, 2 * 9437184, 2 * 4718592, 2 * 9437184, 2 * 1048576]
 
 
+def ncu_traffic(batch):
+    """DRAM bytes per step of the tcgen05 kernel family from the committed `ncu --set full` capture (profiles/*_ncu_traffic.json,
+    written by scripts/ncu_summary.py); None when no capture exists for this batch size."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for f in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if f.endswith("_ncu_traffic.json"):
+            d = json.load(open(os.path.join(pdir, f)))
+            if d.get("batch") == batch:
+                best = {"dram_bytes_per_step": d["family_bytes_per_step"], "launches": len(d["launches"]), "source": "profiles/" + f}
+    return best
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -344,7 +357,7 @@ def _main(real_stdout):
         roof = {"kernel": "tcgen05 conv kernels (%d launches/step: tc_first2_kernel x3, tc_conv_kernel, tc_conv_pair_kernel, tc_head_kernel; fp16 operands with fp16 "
                           "residual planes for AffNet/OriNet, fp32 accumulate in TMEM)" % tc_launches,
                 "bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"],
-                "traffic": None, "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)", "kernel_ms_per_step": tc_ms,
+                "traffic": ncu_traffic(B), "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)", "kernel_ms_per_step": tc_ms,
                 "algorithmic_flop_per_step": tc_flop, "share_of_step": tc_ms / step_ms if step_ms else None,
                 "note": "algorithmic flops = 2*MAC of the reference's fp32 convolutions; the residual-plane products (2-3 MMAs per K step for AffNet/OriNet), the "
                         "rows of zero padding in every 128-row tile and the K=9 first layer padded to K=16 are extra tensor work that is not counted",

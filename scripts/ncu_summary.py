@@ -1,0 +1,113 @@
+"""Turns the ncu reports that scripts/gpu_profile.sh leaves in gpurun_out/ into profiles/<tag>_ncu.md and
+profiles/<tag>_ncu_traffic.json (DRAM bytes per launch of every tcgen05 kernel: bench.py's roofline.traffic).
+
+    python scripts/ncu_summary.py r01            # reads gpurun_out/prof_{tc,misc,blur}.ncu-rep + launches.csv
+"""
+import csv
+import io
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+OUT = os.path.join(ROOT, "gpurun_out")
+COLS = [("time", "gpu__time_duration.sum"), ("dram rd", "dram__bytes_read.sum"), ("dram wr", "dram__bytes_write.sum"),
+        ("dram %", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+        ("tensor %", "sm__inst_executed_pipe_tensor_op_gmma.avg.pct_of_peak_sustained_active|sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active|sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active|sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+        ("sm %", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+        ("smem %", "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed|l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+        ("issue %", "smsp__issue_active.avg.pct_of_peak_sustained_active"), ("L2 hit %", "lts__t_sector_hit_rate.pct"),
+        ("regs", "launch__registers_per_thread"), ("occ %", "sm__warps_active.avg.pct_of_peak_sustained_active"), ("grid", "launch__grid_size")]
+
+
+def raw_rows(rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units, body = rows[0], rows[1], rows[2:]
+    return hdr, units, body
+
+
+def to_bytes(v, unit):
+    f = float(v.replace(",", ""))
+    return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+def short(name):
+    name = re.sub(r"^(void )?(ag::)?(tc::)?", "", name)
+    name = re.sub(r"\(.*$", "", name)
+    return name.replace("(int)", "")
+
+
+def table(rep, md, traffic=None):
+    hdr, units, body = raw_rows(rep)
+    ix = {h: i for i, h in enumerate(hdr)}
+    md.append("| kernel | " + " | ".join(c for c, _ in COLS) + " |")
+    md.append("|---" * (len(COLS) + 1) + "|")
+    for r in body:
+        cells = []
+        for c, keys in COLS:
+            k = next((k for k in keys.split("|") if k in ix), None)
+            if k is None:
+                cells.append("-")
+                continue
+            v, u = r[ix[k]], units[ix[k]]
+            try:
+                v = "%.4g" % float(v.replace(",", ""))
+            except ValueError:
+                pass
+            cells.append(("%s %s" % (v, u)).strip() if c in ("time", "dram rd", "dram wr") else v)
+        name = short(r[ix["Kernel Name"]])
+        md.append("| `%s` | " % name + " | ".join(cells) + " |")
+        if traffic is not None:
+            b = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
+            traffic.append({"kernel": name, "dram_bytes": b})
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    md = ["# %s: `ncu --set full --clock-control none` captures on B200" % tag, "",
+          "Command: `scripts/gpu_profile.sh` (bench.py --batch 16 --no-graph, one launch of every kernel of one step after three warm-up steps); "
+          "this file: `python scripts/ncu_summary.py %s`." % tag,
+          "Times under ncu are cold-cache and serialised: use the ratios (DRAM %, tensor %, issue %), not the absolute times.",
+          "Template arguments: `tc_first2_kernel<C1,COUT,SA,SW,OSA>`, `tc_conv_kernel<CIN,COUT,H,STRIDE,NSPLIT,STAGES,OUT,SA,SW,OSA,FIRST>`, "
+          "`tc_conv_pair_kernel<CIN,COUT,H,STRIDE,STAGES,OUT>` (OUT: 0 plain, 1 phase-split, 2 fp32 NCHW, 3 head operand), `tc_headx_kernel<0 AffNet | 1 OriNet>`.", ""]
+    traffic = []
+    for title, rep, tr in (("tensor-core kernels (AffNet, OriNet, HardNet in launch order)", "prof_tc.ncu-rep", traffic),
+                           ("detector, selection, filters", "prof_misc.ncu-rep", None), ("blur kernels (octave 0 and 1 of one step)", "prof_blur.ncu-rep", None)):
+        path = os.path.join(OUT, rep)
+        if not os.path.isfile(path):
+            continue
+        md += ["## " + title, ""]
+        table(path, md, tr)
+        md.append("")
+    lp = os.path.join(OUT, "launches.csv")
+    if os.path.isfile(lp):
+        rows = [r for r in csv.reader(open(lp)) if len(r) > 5]
+        hdr = next(r for r in rows if "Kernel Name" in r)
+        body = rows[rows.index(hdr) + 1:]
+        kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        agg, total = {}, 0.0
+        for r in body:
+            try:
+                ns = float(r[mv].replace(",", "")) * {"ns": 1, "us": 1e3, "ms": 1e6, "nsecond": 1, "usecond": 1e3, "msecond": 1e6}.get(r[mu], 1)
+            except ValueError:
+                continue
+            k = short(r[kn])
+            a = agg.setdefault(k, [0.0, 0])
+            a[0] += ns; a[1] += 1; total += ns
+        md += ["## launch list (`ncu --metrics gpu__time_duration.sum`, %d launches = warm-up + timed steps; %.1f ms of kernel time)" % (sum(a[1] for a in agg.values()), total / 1e6), "",
+               "| ms | share | launches | kernel |", "|---|---|---|---|"]
+        for k, (ns, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            md.append("| %.3f | %.1f%% | %d | `%s` |" % (ns / 1e6, 100 * ns / total, n, k))
+        md.append("")
+    open(os.path.join(ROOT, "profiles", tag + "_ncu.md"), "w").write("\n".join(md))
+    if traffic:
+        json.dump({"batch": 16, "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, one step", "launches": traffic,
+                   "family_bytes_per_step": sum(t["dram_bytes"] for t in traffic)}, open(os.path.join(ROOT, "profiles", tag + "_ncu_traffic.json"), "w"), indent=1)
+    print("\n".join(md[:12]))
+
+
+if __name__ == "__main__":
+    main()

@@ -245,6 +245,18 @@ def test_nets_vs_oracle(L, nets, engine):
             aff.set_engine(L.ENGINE_TC); ori.set_engine(L.ENGINE_TC)
 
 
+def test_nets_batching_invariance(L, nets):
+    """Tile boundaries of the tensor-core path (2 patches per CTA pair, 128 per head tile, persistent strides over the SMs):
+    every patch's result is bit-identical whatever batch it is evaluated in."""
+    aff, ori, hn = nets
+    g = torch.Generator().manual_seed(21)
+    P = (torch.rand(513, 1, 32, 32, generator=g) * 255).to(DEV)
+    for m in (aff, ori, hn):
+        full = m(P)
+        for lo, hi in ((0, 1), (1, 130), (130, 387), (386, 513), (512, 513)):
+            assert torch.equal(m(P[lo:hi].contiguous()), full[lo:hi]), (type(m).__name__, lo, hi)
+
+
 def test_shape_filter_identical_given_A(L):
     lib = L.lib()
     z = gold("graf_crop.npz")
