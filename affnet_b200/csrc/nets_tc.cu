@@ -38,7 +38,8 @@ static int launch_tc(const __half* in, void* out, const __half* w, const float* 
         configured = true;
     }
     ConvArgs a;
-    a.in = in; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.n = n; a.group = group; a.count = count;
+    a.in = in; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.prof_id = 0; a.n = n; a.group = group; a.count = count;
+    a.prof_id = (H == 32) ? (FIRST ? 0 : 2) : (H == 16 ? (STRIDE == 1 ? 3 : 4) : 5);
     int gx = num_sms() / NSPLIT;
     if (gx > n) gx = n;
     if (gx < 1) gx = 1;
@@ -60,7 +61,7 @@ static int launch_first2(void* out, const __half* w, const float* b, float inv_s
         configured = true;
     }
     ConvArgs a;
-    a.in = nullptr; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.n = n; a.group = group; a.count = count;
+    a.in = nullptr; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.prof_id = 0; a.n = n; a.group = group; a.count = count;
     int gx = num_sms();
     if (gx > n) gx = n;
     if (gx < 1) gx = 1;
@@ -81,7 +82,7 @@ static int launch_pair(const __half* in, void* out, const __half* w, const float
         configured = true;
     }
     ConvArgs a;
-    a.in = in; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.n = n; a.group = group; a.count = count;
+    a.in = in; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.prof_id = 0; a.n = n; a.group = group; a.count = count;
     int pairs = num_sms() / 2;
     if (pairs > (n + 1) / 2) pairs = (n + 1) / 2;
     if (pairs < 1) pairs = 1;
@@ -231,6 +232,8 @@ int tc_split_w(int kind) { return kind == AG_NET_HARDNET ? 0 : 1; }
 #ifdef AG_ROLE_PROF
 // developer-only: per-CTA role cycle counters of the last tc_first2_kernel launch (tc_first.cuh)
 extern "C" int ag_debug_role_prof(unsigned long long* out) {
-    return cudaMemcpyFromSymbol(out, ag::tc::g_role_prof, sizeof(unsigned long long) * 160 * 20) == cudaSuccess ? 0 : 1;
+    if (cudaMemcpyFromSymbol(out, ag::tc::g_role_prof, sizeof(unsigned long long) * 8 * 160 * 20) != cudaSuccess) return 1;
+    void* p = nullptr;
+    return (cudaGetSymbolAddress(&p, ag::tc::g_role_prof) == cudaSuccess && cudaMemset(p, 0, sizeof(unsigned long long) * 8 * 160 * 20) == cudaSuccess) ? 0 : 1;
 }
 #endif

@@ -19,6 +19,20 @@
 namespace ag {
 namespace tc {
 
+// Developer-only role profiler (build with -DAG_ROLE_PROF, scripts/role_prof.sh): cycles every warp role spends in its loop and
+// waiting on each of its barriers, per CTA.  Compiled out of the product library.
+#ifdef AG_ROLE_PROF
+__device__ unsigned long long g_role_prof[8][160][20];   // [kernel slot: 0 tc_first2, l = conv layer l+1][CTA][role*5 + k]
+#define RP_DECL unsigned long long rp_t0 = clock64(), rp_w[4] = {0, 0, 0, 0}
+#define RP_WAIT(i, stmt) do { const unsigned long long rp_t = clock64(); stmt; rp_w[i] += clock64() - rp_t; } while (0)
+#define RP_STORE(slot, role) do { if (lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6 || warp == 10)) { unsigned long long* d_ = g_role_prof[slot][blockIdx.x] + (role) * 5; \
+    d_[0] = clock64() - rp_t0; d_[1] = rp_w[0]; d_[2] = rp_w[1]; d_[3] = rp_w[2]; d_[4] = rp_w[3]; } } while (0)
+#else
+#define RP_DECL
+#define RP_WAIT(i, stmt) stmt
+#define RP_STORE(slot, role)
+#endif
+
 enum LayoutKind { PLAIN = 0, PHASE = 1, FINAL = 2, HEADL = 3 };  // HEADL: fp16 [patch/128][pixel*C/8 + c/8][patch%128][8], the A operand of the 8x8-head GEMM
 
 // Pixel-slot geometry of an activation buffer that is the INPUT of a layer with `stride` on an HxH map.
@@ -156,6 +170,7 @@ struct ConvArgs {
     void* out;            // next layer's canonical fp16 buffer, or fp32 [n][COUT][HOUT][HOUT]
     const __half* wpk;    // [NSPLIT][9][CIN/8][hi rows | lo rows][8]: (1+SW)*COUT/NSPLIT rows per K chunk
     const float* bias;    // [COUT]
+    int prof_id;          // developer role profiler: slot of g_role_prof this launch reports to
     float inv_scale;      // wpk holds the weights times a power of two (fp16 residuals stay normal); accumulators are multiplied by its inverse
     int n, group;
     const int* count;
@@ -239,10 +254,11 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
             mbar_expect_tx(wbar, Cfg::W_BYTES);
             bulk_g2s(sW, reinterpret_cast<const unsigned char*>(a.wpk) + (size_t)split * Cfg::W_BYTES, Cfg::W_BYTES, wbar);
             int it = 0;
+            RP_DECL;
             for (int pi = blockIdx.x; pi < a.n && !FIRST; pi += gridDim.x) {
                 if (!valid(pi)) continue;
                 const int s = it % STAGES;
-                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                RP_WAIT(0, mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1));
                 constexpr int G = KC * (1 + SA);
                 mbar_expect_tx(&full[s], (uint32_t)G * In::USED * 16u);
                 const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.in) + (size_t)pi * Cfg::IN_BYTES;
@@ -251,6 +267,7 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
                     bulk_g2s(sIn + (size_t)s * Cfg::IN_BYTES + (size_t)g * In::NPIX * 16, gsrc + (size_t)g * In::NPIX * 16, In::USED * 16u, &full[s]);
                 it++;
             }
+            RP_STORE(a.prof_id, 3);
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues =====
@@ -261,16 +278,17 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
         tc_fence_after();
         const uint32_t w_lo = desc_lo(smem_u32(sW), Cfg::ACCW * 16u);
         int it = 0, tcnt = 0;
+        RP_DECL;
         for (int pi = blockIdx.x; pi < a.n; pi += gridDim.x) {
             if (!valid(pi)) continue;
             const int s = it % STAGES;
-            mbar_wait(&full[s], (it / STAGES) & 1);
+            RP_WAIT(0, mbar_wait(&full[s], (it / STAGES) & 1));
             tc_fence_after();
             const uint32_t in_lo = desc_lo(smem_u32(sIn + (size_t)s * Cfg::IN_BYTES), In::NPIX * 16u);
 #pragma unroll 1
             for (int t = 0; t < TILES; t++, tcnt++) {
                 const int ab = tcnt % NACC;
-                mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1);
+                RP_WAIT(1, mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1));
                 tc_fence_after();
                 if (leader) {
                     const uint32_t d_tmem = tmem + (uint32_t)(ab * Cfg::ACCW);
@@ -295,6 +313,7 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
             __syncwarp();
             it++;
         }
+        RP_STORE(a.prof_id, 0);
     } else if (FIRST && warp >= 6) {
         // ===== fused first layer: sampler (or patch load) -> input_norm -> conv3x3(1 -> CIN) + ReLU -> fp16 stage =====
         static_assert(!FIRST || (H == 32 && STRIDE == 1), "the first conv layer feeds a stride-1 32x32 layer");
@@ -420,6 +439,7 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
         const int q = warp & 3;
         const int et = (warp - 2) * 32 + lane;  // 0..127
         int tcnt = 0;
+        RP_DECL;
         for (int pi = blockIdx.x; pi < a.n; pi += gridDim.x) {
             if (!valid(pi)) continue;
             unsigned char* outp = reinterpret_cast<unsigned char*>(a.out) + (size_t)pi * Cfg::OUT_BYTES;
@@ -443,7 +463,7 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
 #pragma unroll 1
             for (int t = 0; t < TILES; t++, tcnt++) {
                 const int ab = tcnt % NACC;
-                mbar_wait(&tfull[ab], (tcnt / NACC) & 1);
+                RP_WAIT(0, mbar_wait(&tfull[ab], (tcnt / NACC) & 1));
                 tc_fence_after();
                 const bool t64 = In::TAIL64 && t == TILES - 1;
                 const int m = t * 128 + (t64 ? q * 16 : q * 32) + lane;
@@ -527,6 +547,7 @@ __global__ void __launch_bounds__(FIRST ? 448 : 192, 1) tc_conv_kernel(const Con
                 }
             }
         }
+        RP_STORE(a.prof_id, 1);
     }
     tc_fence_before();
     __syncthreads();

@@ -19,20 +19,6 @@
 namespace ag {
 namespace tc {
 
-// Developer-only role profiler (build with -DAG_ROLE_PROF, scripts/role_prof.sh): cycles every warp role spends in its loop and
-// waiting on each of its barriers, per CTA.  Compiled out of the product library.
-#ifdef AG_ROLE_PROF
-__device__ unsigned long long g_role_prof[160][20];
-#define RP_DECL unsigned long long rp_t0 = clock64(), rp_w[4] = {0, 0, 0, 0}
-#define RP_WAIT(i, stmt) do { const unsigned long long rp_t = clock64(); stmt; rp_w[i] += clock64() - rp_t; } while (0)
-#define RP_STORE(role) do { if (lane == 0 && (warp == 1 || warp == 2 || warp == 6 || warp == 10)) { unsigned long long* d_ = g_role_prof[blockIdx.x] + (role) * 5; \
-    d_[0] = clock64() - rp_t0; d_[1] = rp_w[0]; d_[2] = rp_w[1]; d_[3] = rp_w[2]; d_[4] = rp_w[3]; } } while (0)
-#else
-#define RP_DECL
-#define RP_WAIT(i, stmt) stmt
-#define RP_STORE(role)
-#endif
-
 template <int C1, int COUT, int SA, int SW, int OSA>
 struct FirstCfg {
     using In = InLay<32, 1>;     // layout of the stage (input of layer 2)
@@ -213,7 +199,7 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
             it++;
             pi = pn;
         }
-        RP_STORE(0);
+        RP_STORE(0, 0);
     } else if (warp < 6) {
         // ===== layer-2 epilogue: TMEM -> bias + ReLU -> fp16 -> global (layout of the stride-2 consumer) =====
         const int q = warp & 3, et = (warp - 2) * 32 + lane;
@@ -290,7 +276,7 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
                 }
             }
         }
-        RP_STORE(1);
+        RP_STORE(0, 1);
     } else if (warp < 10) {
         // ===== layer-1 epilogue: TMEM -> bias + ReLU -> fp16 (hi [+lo]) -> shared-memory stage of layer 2 =====
         const int q = warp & 3;
@@ -352,7 +338,7 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&full[s]);
         }
-        RP_STORE(2);
+        RP_STORE(0, 2);
     } else {
         // ===== producers: sampler (or patch load) -> input_norm -> sliding-window planes P_hi / P_lo =====
         const int pt = threadIdx.x - 320;   // 0..127
@@ -438,7 +424,7 @@ __global__ void __launch_bounds__(448, 1) tc_first2_kernel(const ConvArgs a, con
             it++;
             pi = pn;
         }
-        RP_STORE(3);
+        RP_STORE(0, 3);
     }
     tc_fence_before();
     __syncthreads();

@@ -22,6 +22,9 @@ ROLES = [("mma issuer", ["p_full", "c1_empty", "full(L1 epi done)", "tempty"]),
          ("L2 epilogue", ["tfull", "-", "-", "-"]),
          ("L1 epilogue", ["empty(L2 mma done)", "c1_full", "-", "-"]),
          ("producer", ["p_empty", "gather latency", "-", "-"])]
+CONV_ROLES = [("mma issuer", ["full (input landed)", "tempty (epilogue drained)", "-", "-"]),
+              ("epilogue", ["tfull (MMAs done)", "-", "-", "-"]), None,
+              ("loader", ["empty (stage free)", "-", "-", "-"])]
 
 
 def main():
@@ -40,18 +43,26 @@ def main():
         torch.cuda.synchronize()
         launches = _lib.profile(lambda: m(P))
         torch.cuda.synchronize()
-        buf = np.zeros((160, 20), dtype=np.uint64)
+        buf = np.zeros((8, 160, 20), dtype=np.uint64)
         assert L.ag_debug_role_prof(buf.ctypes.data_as(C.c_void_p)) == 0
-        t = buf[:148].astype(np.float64)
         per_cta = n / 148.0
-        print("== %s: %d patches, %.1f per CTA; launches: %s" % (name, n, per_cta, [(k, round(v, 3)) for k, v in launches][:2]))
-        for r, (rn, wn) in enumerate(ROLES):
-            tot = t[:, r * 5].mean()
-            line = "  %-12s total %8.0f clk/patch" % (rn, tot / per_cta)
-            for i in range(4):
-                if wn[i] != "-":
-                    line += " | wait %s %6.0f" % (wn[i], t[:, r * 5 + 1 + i].mean() / per_cta)
-            print(line)
+        print("== %s: %d patches, %.1f per CTA; launches: %s" % (name, n, per_cta, [(k, round(v, 3)) for k, v in launches]))
+        for slot in range(6):
+            t = buf[slot, :148].astype(np.float64)
+            if t.sum() == 0:
+                continue
+            print(" kernel slot %d (%s)" % (slot, "tc_first2: layers 1+2" if slot == 0 else "tc_conv layer %d" % (slot + 1)))
+            for r, role in enumerate(ROLES if slot == 0 else CONV_ROLES):
+                if role is None:
+                    continue
+                rn, wn = role
+                tot = t[:, r * 5].mean()
+                line = "  %-12s total %8.0f clk/patch" % (rn, tot / per_cta)
+                for i in range(4):
+                    if wn[i] != "-":
+                        line += " | wait %s %6.0f" % (wn[i], t[:, r * 5 + 1 + i].mean() / per_cta)
+                print(line)
+        buf[:] = 0
 
 
 if __name__ == "__main__":
