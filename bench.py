@@ -296,7 +296,14 @@ def _main(real_stdout):
             e0.record(); fn(); e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
-        clocks = sampler.stop() if sampler else None
+        clocks = None
+        if sampler:
+            # nvidia-smi can take longer to start than K short steps last: keep the same load running (untimed) until a few samples exist
+            extra, t_end = 0, time.time() + 4.0
+            while len(sampler.lines) < 5 and time.time() < t_end:
+                fn(); torch.cuda.synchronize(); extra += 1
+            clocks = sampler.stop()
+            clocks["extra_load_steps_for_sampling"] = extra
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
