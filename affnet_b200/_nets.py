@@ -28,7 +28,7 @@ class _NativeNet(nn.Module):
         super().__init__()
         self._handle = None
         self._handle_key = None
-        self._engine = None   # None = library default (HardNet: tensor cores, AffNet/OriNet: exact fp32)
+        self._engine = None   # None = library default (tensor cores for all three nets)
 
     # -- weights ------------------------------------------------------------------------------------------
     def _blob(self):
@@ -60,7 +60,8 @@ class _NativeNet(nn.Module):
         return self._handle
 
     def set_engine(self, engine):
-        """engine: L.ENGINE_SIMT (exact fp32) or L.ENGINE_TC (tcgen05, fp16 operands / fp32 accumulate)."""
+        """engine: L.ENGINE_SIMT (exact fp32 CUDA cores), L.ENGINE_TC (tcgen05, default) or L.ENGINE_TC_EXACT (AffNet / OriNet:
+        residual planes everywhere + fp32 heads); see include/affnet_b200.h."""
         self._engine = engine
         if self._handle is not None:
             L.check(L.lib().ag_net_set_engine(self._handle, engine))

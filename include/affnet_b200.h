@@ -163,10 +163,12 @@ typedef struct ag_net ag_net_t;
 int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out);
 void ag_net_destroy(ag_net_t* net);
 size_t ag_net_blob_floats(int kind);
-/* Compute engine of the six 3x3 conv layers: 0 = exact fp32 SIMT, 1 = tcgen05 tensor cores (fp16 operands, fp32
- * accumulation; the K=9 first layer and the 8x8 head stay fp32; AffNet adds the fp16 residual of the weights,
- * OriNet the residuals of weights and activations: fp32-grade results); 2 = as 1 but AffNet also carries the activation
- * residuals (fp32-grade A matrices at twice the activation traffic).  Default: 1 for all three nets. */
+/* Compute engine: 0 = exact fp32 SIMT (needs materialised patches); 1 = tcgen05 tensor cores: fp16 operands, fp32
+ * accumulation in TMEM, all six conv layers and the 8x8 heads as MMAs; the first layer and the AffNet/OriNet heads carry fp16
+ * residual planes of both operands, AffNet's layers 2-6 the residual of the weights, OriNet's the residuals of weights and
+ * activations (measured error vs the fp32 reference: A 1.9e-4, angle 2.8e-5 rad, descriptors 5.8e-4); 2 = residuals of weights
+ * and activations for AffNet too and fp32 FMA-chain heads (A 2e-6, angle 3e-6 rad; AffNet/OriNet only).
+ * Default: 1 for all three nets. */
 int ag_net_set_engine(ag_net_t* net, int engine);
 int ag_net_get_engine(const ag_net_t* net);
 /* Scratch bytes for a forward over n patches. */
