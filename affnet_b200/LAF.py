@@ -78,3 +78,21 @@ def LAFs2ell(in_LAFs):
         M = u @ np.diag(W) @ u.T
         ell[i] = [LAFs[i, 0, 2], LAFs[i, 1, 2], M[0, 0], M[0, 1], M[1, 1]]
     return ell
+
+
+def LAFs2ellT(LAFs):
+    """LAF.py:35-51 on the device (`ag_lafs_to_ell`): [n,2,3] pixel LAFs -> [n,5] rows (x, y, a, b, c), the Oxford-affine
+    format hesaffBaum.py:46-48 writes."""
+    if not LAFs.is_cuda:
+        raise L.AffnetB200Error("LAFs2ellT: CUDA tensor expected (there is no CPU path)")
+    LAFs = LAFs.contiguous().float()
+    n = LAFs.size(0)
+    ell = torch.empty(n, 5, device=LAFs.device)
+    if n:
+        L.check(L.lib().ag_lafs_to_ell(L.ptr(LAFs), n, L.ptr(ell), L.stream_ptr()))
+    return ell
+
+
+def save_ells(fname, ells):
+    """The reference's text output (hesaffBaum.py:48): one `x y a b c` row per keypoint, %10.10f."""
+    np.savetxt(fname, ells.detach().cpu().numpy() if isinstance(ells, torch.Tensor) else np.asarray(ells), delimiter=" ", fmt="%10.10f")

@@ -82,6 +82,7 @@ PROTOTYPES = {
     "ag_affine_shape_filter": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "ag_lafs_apply_rotation": (i32, [vp, vp, i32, vp]),
     "ag_lafs_scale": (i32, [vp, vp, i32, f32, f32, f32, vp]),
+    "ag_lafs_to_ell": (i32, [vp, i32, vp, vp]),
     "ag_circular_gauss_kernel": (i32, [i32, f64, vp]),
     "ag_orientation_hist": (i32, [vp, i32, i32, vp, vp, vp]),
     "ag_baumberg_shape": (i32, [vp, i32, i32, vp, vp, vp]),

@@ -141,6 +141,29 @@ __global__ void lafs_scale_kernel(const float* __restrict__ in, float* __restric
     O[3] = __fmul_rn(L[3], ac); O[4] = __fmul_rn(L[4], ac); O[5] = __fmul_rn(L[5], yc);
 }
 
+// LAFs2ellT (LAF.py:35-51) with the closed-form 2x2 SVD of bsvd2x2 (LAF.py:106-144): one thread per keypoint.  Only U and
+// the singular values of A / scale enter the result: ell = (x, y, M00, M01, M11), M = U diag(1 / (scale^2 s_i^2)) U^T.
+__global__ void lafs_to_ell_kernel(const float* __restrict__ lafs, float* __restrict__ ell, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* L = lafs + (size_t)i * 6;
+    const float scale = sqrtf(L[0] * L[4] - L[1] * L[3] + 1e-10f);
+    const float a00 = L[0] / scale, a01 = L[1] / scale, a10 = L[3] / scale, a11 = L[4] / scale;
+    // Su = A A^T
+    const float s00 = a00 * a00 + a01 * a01, s01 = a00 * a10 + a01 * a11, s11 = a10 * a10 + a11 * a11;
+    const float phi = 0.5f * atan2f(s01 + s01 + 1e-12f, s00 - s11 + 1e-12f);
+    const float c = cosf(phi), sn = sinf(phi);   // U = [[c, -s], [s, c]]
+    const float sum = s00 + s11;
+    const float dif = sqrtf((s00 - s11) * (s00 - s11) + 4.0f * s01 * s01 + 1e-12f);
+    const float sig0 = sqrtf((sum + dif) / 2.0f), sig1 = sqrtf((sum - dif) / 2.0f);
+    const float w0 = 1.0f / (scale * scale * sig0 * sig0), w1 = 1.0f / (scale * scale * sig1 * sig1);
+    float* o = ell + (size_t)i * 5;
+    o[0] = L[2]; o[1] = L[5];
+    o[2] = c * w0 * c + sn * w1 * sn;          // (U W U^T)[0][0]
+    o[3] = c * w0 * sn - sn * w1 * c;          // [0][1]
+    o[4] = sn * w0 * sn + c * w1 * c;          // [1][1]
+}
+
 }  // namespace ag
 
 using namespace ag;
@@ -188,6 +211,14 @@ int ag_lafs_scale(const float* d_in, float* d_out, int n, float a_coef, float x_
     if (n <= 0) return AG_OK;
     lafs_scale_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, n, a_coef, x_coef, y_coef);
     AG_CHECK_LAUNCH("lafs_scale_kernel");
+    return AG_OK;
+}
+
+int ag_lafs_to_ell(const float* d_lafs, int n, float* d_ell, void* stream) {
+    AG_REQUIRE(d_lafs && d_ell, "NULL argument");
+    if (n <= 0) return AG_OK;
+    lafs_to_ell_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d_lafs, d_ell, n);
+    AG_CHECK_LAUNCH("lafs_to_ell_kernel");
     return AG_OK;
 }
 

@@ -209,6 +209,10 @@ int ag_affine_shape_filter(const float* d_A, const float* d_resp, const float* d
 /* LAF_A <- LAF_A * R  then (optionally) denormalise to pixels of a WxH image.  d_lafs [n,2,3] in/out. */
 int ag_lafs_apply_rotation(float* d_lafs, const float* d_R, int n, void* stream);
 int ag_lafs_scale(const float* d_in, float* d_out, int n, float a_coef, float x_coef, float y_coef, void* stream);
+/* Output format of the reference's writers (hesaffBaum.py:46-48): replaces LAFs2ellT (LAF.py:35-51, bsvd2x2 :106-144).
+ * d_lafs [n,2,3] in pixels -> d_ell [n,5] = (x, y, a, b, c) with a u^2 + 2 b u v + c v^2 = 1.  A LAF with a negative
+ * determinant gives NaN, as in the reference. */
+int ag_lafs_to_ell(const float* d_lafs, int n, float* d_ell, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Hand-crafted estimators (SURVEY.md §8f "next" rows): what the reference uses when OriNet / AffNet are None.

@@ -647,3 +647,48 @@ def match_snn(desc1, desc2, ratio=0.8):
     sec, _ = torch.min(dist, 1)
     mask = (mn / (sec + 1e-8)) <= ratio
     return torch.arange(idx2.size(0))[mask], idx2[mask], mn, sec
+
+
+# ---------------------------------------------------------------------------------------------
+# output formats
+# ---------------------------------------------------------------------------------------------
+def bsvd2x2(As):
+    """Closed-form batched 2x2 SVD (LAF.py:106-144): U from atan2 on A A^T, V from atan2 on A^T A with the sign matrix of
+    U^T A W folded in, singular values from the eigenvalues of A A^T.  Returns U, SIG, V as [n,2,2]."""
+    As = As.float()
+    Su = torch.bmm(As, As.permute(0, 2, 1))
+    phi = 0.5 * torch.atan2(Su[:, 0, 1] + Su[:, 1, 0] + 1e-12, Su[:, 0, 0] - Su[:, 1, 1] + 1e-12)
+    U = torch.zeros(As.size(0), 2, 2)
+    U[:, 0, 0] = torch.cos(phi); U[:, 1, 1] = torch.cos(phi); U[:, 0, 1] = -torch.sin(phi); U[:, 1, 0] = torch.sin(phi)
+    Sw = torch.bmm(As.permute(0, 2, 1), As)
+    theta = 0.5 * torch.atan2(Sw[:, 0, 1] + Sw[:, 1, 0] + 1e-12, Sw[:, 0, 0] - Sw[:, 1, 1] + 1e-12)
+    Wm = torch.zeros(As.size(0), 2, 2)
+    Wm[:, 0, 0] = torch.cos(theta); Wm[:, 1, 1] = torch.cos(theta); Wm[:, 0, 1] = -torch.sin(theta); Wm[:, 1, 0] = torch.sin(theta)
+    SUsum = Su[:, 0, 0] + Su[:, 1, 1]
+    SUdif = torch.sqrt((Su[:, 0, 0] - Su[:, 1, 1]) ** 2 + 4 * Su[:, 0, 1] * Su[:, 1, 0] + 1e-12)
+    SIG = torch.zeros(As.size(0), 2, 2)
+    SIG[:, 0, 0] = torch.sqrt((SUsum + SUdif) / 2.0)
+    SIG[:, 1, 1] = torch.sqrt((SUsum - SUdif) / 2.0)
+    S = torch.bmm(torch.bmm(U.permute(0, 2, 1), As), Wm)
+    C = torch.sign(S)
+    C[:, 0, 1] = 0; C[:, 1, 0] = 0
+    return U, SIG, torch.bmm(Wm, C)
+
+
+def lafs_to_ell_t(LAFs):
+    """LAFs2ellT (LAF.py:35-51): [n,2,3] pixel LAFs -> [n,5] = (x, y, a, b, c) of the ellipse a u^2 + 2 b u v + c v^2 = 1,
+    the Oxford-affine text format written by hesaffBaum.py:46-48."""
+    LAFs = LAFs.float()
+    n = LAFs.size(0)
+    ell = torch.zeros(n, 5)
+    if n == 0:
+        return ell
+    scale = torch.sqrt(LAFs[:, 0, 0] * LAFs[:, 1, 1] - LAFs[:, 0, 1] * LAFs[:, 1, 0] + 1e-10)
+    u, Wd, _ = bsvd2x2(LAFs[:, 0:2, 0:2] / scale.view(-1, 1, 1))
+    Wd = Wd.clone()
+    Wd[:, 0, 0] = 1.0 / (scale * scale * Wd[:, 0, 0] ** 2)
+    Wd[:, 1, 1] = 1.0 / (scale * scale * Wd[:, 1, 1] ** 2)
+    A = torch.bmm(torch.bmm(u, Wd), u.permute(0, 2, 1))
+    ell[:, 0] = LAFs[:, 0, 2]; ell[:, 1] = LAFs[:, 1, 2]
+    ell[:, 2] = A[:, 0, 0]; ell[:, 3] = A[:, 0, 1]; ell[:, 4] = A[:, 1, 1]
+    return ell

@@ -14,6 +14,8 @@ changes.  Outputs (all .npz, compressed):
   face_patches.npz   first 64 patches of examples/just_shape/img/face.png -> AffNetFast matrices
   nets_random.npz    the three nets on 32 random patches (input + outputs)
   handcrafted.npz    OrientationDetector / AffineShapeEstimator on 19x19 patches; default detector (OriNet=None) end to end
+  ell.npz            LAFs2ellT (the Oxford-affine output of hesaffBaum.py) on the graf crop's final LAFs + synthetic LAFs
+                     (`python tests/golden/make_golden.py ell` regenerates only this file from graf_crop.npz)
 """
 import contextlib
 import io
@@ -167,5 +169,22 @@ def main():
              hardnet_desc=hn(P))
 
 
+def make_ell():
+    m = R.ref_modules()
+    z = np.load(os.path.join(HERE, "graf_crop.npz"))
+    g = torch.Generator().manual_seed(11)
+    A = torch.randn(64, 2, 2, generator=g) * 6.0
+    A[:, 0, 0] = A[:, 0, 0].abs() + 4.0; A[:, 1, 1] = A[:, 1, 1].abs() + 4.0       # positive determinant
+    syn = torch.cat([A, torch.rand(64, 2, 1, generator=g) * 300.0], dim=2)
+    lafs = torch.cat([torch.from_numpy(z["ori_dLAFs"]), torch.from_numpy(z["noori_dLAFs"]), syn]).float()
+    with torch.no_grad():
+        ell = m["LAF"].LAFs2ellT(lafs)
+    save("ell.npz", lafs=lafs, ell=ell)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ell":
+        make_ell()
+    else:
+        main()
+        make_ell()

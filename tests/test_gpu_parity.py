@@ -421,3 +421,22 @@ def test_snn_matcher_8f(L, nets):
     assert (mn.cpu() - omn).abs().max() < 1e-5 and (sec.cpu() - osec).abs().max() < 1e-5
     assert torch.equal(i1.cpu(), o1) and torch.equal(i2.cpu(), o2)
     assert 0 < i1.numel() <= 700
+
+
+def test_lafs2ell_t_8f(L, tmp_path):
+    """8f row 4: LAFs2ellT on the device against the golden from the unmodified reference (fp32 closed-form SVD: 1e-5 relative),
+    NaN for the degenerate row as in the reference, and the text writer."""
+    from affnet_b200.LAF import LAFs2ellT, save_ells
+    z = gold("ell.npz")
+    g = torch.from_numpy(z["ell"])
+    e = LAFs2ellT(torch.from_numpy(z["lafs"]).to(DEV)).cpu()
+    assert torch.equal(torch.isnan(e), torch.isnan(g))
+    ok = ~torch.isnan(g).any(dim=1)
+    rel = ((e[ok] - g[ok]).abs() / g[ok].abs().clamp_min(1e-6)).max().item()
+    print("\nLAFs2ellT: max relative error %.2e over %d keypoints" % (rel, int(ok.sum())))
+    assert torch.equal(e[ok][:, :2], g[ok][:, :2]) and rel < 2e-5
+    assert LAFs2ellT(torch.zeros(0, 2, 3, device=DEV)).shape == (0, 5)
+    f = tmp_path / "ells.txt"
+    save_ells(str(f), e[ok])
+    back = np.loadtxt(str(f))
+    assert back.shape == (int(ok.sum()), 5) and np.allclose(back, e[ok].numpy(), rtol=0, atol=1e-9 + 1e-7 * np.abs(e[ok].numpy()).max())

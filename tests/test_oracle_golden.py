@@ -169,3 +169,14 @@ def test_distance_matrix_vs_reference_if_present():
     g = torch.Generator().manual_seed(5)
     a, b = torch.randn(50, 128, generator=g), torch.randn(70, 128, generator=g)
     assert torch.equal(O.distance_matrix_vector(a, b), ref.distance_matrix_vector(a, b))
+
+
+def test_lafs2ell_t_matches_reference_bit_exactly():
+    """8f row 4: the Oxford-affine output format.  One synthetic LAF has a negative determinant: NaN, as in the reference."""
+    z = gold("ell.npz")
+    e = O.lafs_to_ell_t(torch.from_numpy(z["lafs"]))
+    g = torch.from_numpy(z["ell"])
+    assert torch.equal(torch.isnan(e), torch.isnan(g)) and int(torch.isnan(g).any(dim=1).sum()) == 1
+    ok = ~torch.isnan(g).any(dim=1)
+    assert torch.equal(e[ok], g[ok])
+    assert O.lafs_to_ell_t(torch.zeros(0, 2, 3)).shape == (0, 5)
