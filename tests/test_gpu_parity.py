@@ -432,8 +432,9 @@ def test_lafs2ell_t_8f(L, tmp_path):
     e = LAFs2ellT(torch.from_numpy(z["lafs"]).to(DEV)).cpu()
     assert torch.equal(torch.isnan(e), torch.isnan(g))
     ok = ~torch.isnan(g).any(dim=1)
-    rel = ((e[ok] - g[ok]).abs() / g[ok].abs().clamp_min(1e-6)).max().item()
-    print("\nLAFs2ellT: max relative error %.2e over %d keypoints" % (rel, int(ok.sum())))
+    scale = g[ok][:, 2:].abs().max(dim=1, keepdim=True).values      # b is ~0 for near-circular regions: compare against the matrix scale
+    rel = ((e[ok][:, 2:] - g[ok][:, 2:]).abs() / scale).max().item()
+    print("\nLAFs2ellT: max error %.2e of the ellipse matrix scale over %d keypoints" % (rel, int(ok.sum())))
     assert torch.equal(e[ok][:, :2], g[ok][:, :2]) and rel < 2e-5
     assert LAFs2ellT(torch.zeros(0, 2, 3, device=DEV)).shape == (0, 5)
     f = tmp_path / "ells.txt"
