@@ -49,6 +49,42 @@ def test_two_rank_gather_and_timing():
     assert res == [(0, True), (1, True)]
 
 
+def _exchange_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from affnet_b200.exchange import DescriptorExchange
+    B, K = 3, 5
+    x = DescriptorExchange(world, B, K, torch.device("cpu"))
+
+    def step_data(r, step):
+        g = torch.Generator().manual_seed(100 * step + r)
+        return torch.rand(B, K, 2, 3, generator=g), torch.rand(B, K, 128, generator=g), torch.randint(1, K + 1, (B,), generator=g, dtype=torch.int32)
+
+    for step in range(5):                                             # more steps than staging slots: slots are reused
+        x.submit(*step_data(rank, step))
+    x.drain()
+    gd, gl, gc = x.last()
+    ok = True
+    for r in range(world):
+        l, d, c = step_data(r, 4)
+        ok = ok and torch.equal(gd[r * B:(r + 1) * B], d) and torch.equal(gl[r * B:(r + 1) * B], l) and torch.equal(gc[r * B:(r + 1) * B], c)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_pipelined_descriptor_exchange():
+    """affnet_b200.exchange.DescriptorExchange (what bench.py runs per step at N > 1) on two gloo ranks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + (os.getpid() % 500)
+    ps = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(60) for p in ps]
+    assert res == [(0, True), (1, True)]
+
+
 def test_shards_are_disjoint_and_cover():
     seen = []
     for r in range(8):
