@@ -73,12 +73,15 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append((time.time(), l)) for l in self.proc.stdout], daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def in_window(self, t0, t1):
+        return sum(1 for t, _ in self.lines if t0 <= t <= t1)
+
+    def stop(self, window=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -88,7 +91,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
-        for l in self.lines:
+        for t, l in self.lines:
+            if window is not None and not (window[0] <= t <= window[1]):
+                continue
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
                 continue
@@ -215,6 +220,9 @@ def _main(real_stdout):
     a.load_state_dict(sd["affnet"]); o.load_state_dict(sd["orinet"]); h.load_state_dict(sd["hardnet"])
     a, o, h = a.eval().to(dev), o.eval().to(dev), h.eval().to(dev)
     B = args.batch
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()   # nvidia-smi needs a few hundred ms to deliver its first sample: start it long before the timed region
     pipe = DetectDescribePipeline(B, H, W, a, h, o, num_features=K, do_ori=True, device=dev)
     host_imgs = make_images(B, 1234 + rank * B).pin_memory()
     dev_imgs = host_imgs.to(dev)
@@ -288,8 +296,7 @@ def _main(real_stdout):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
-        if sampler:
-            sampler.start()
+        t_begin = time.time()
         evs = []
         for _ in range(steps):
             flush.fill_(1.0)                                  # L2 flush between timed iterations (outside the events)
@@ -301,15 +308,16 @@ def _main(real_stdout):
             e0.record(); xchg.drain(); e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
+        t_stop = time.time()
         clocks = None
         if sampler:
-            # nvidia-smi can take longer to start than K short steps last: keep the same load running (untimed) until a few samples exist
-            # (rank 0 only: the load must not contain collectives, so it is the bare pipeline step, not fn)
+            # The sampler runs since before the warm-up; only samples that arrived inside the timed region count.  If the region was
+            # too short for three of them, the same load keeps running (untimed, rank 0 only, hence without collectives) until it is.
             extra, t_end = 0, time.time() + 4.0
-            while len(sampler.lines) < 5 and time.time() < t_end:
+            while sampler.in_window(t_begin, time.time()) < 3 and time.time() < t_end:
                 (pipe.replay(dev_imgs) if use_graph else pipe.run(dev_imgs)); torch.cuda.synchronize(); extra += 1
-            clocks = sampler.stop()
-            clocks["extra_load_steps_for_sampling"] = extra
+            clocks = sampler.stop(window=(t_begin, time.time() if extra else t_stop))
+            clocks["sampled"] = "inside the timed region" if extra == 0 else "timed region + %d extra untimed steps of the same load" % extra
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -319,7 +327,6 @@ def _main(real_stdout):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), clocks
 
-    sampler = ClockSampler(local) if rank == 0 else None
     total_ms, clocks = timed(step_device, args.steps, args.warmup, sampler)
     pipe.check()
     if xchg:   # the exchange delivered this rank's own block intact and every rank's counts
