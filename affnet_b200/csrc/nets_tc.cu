@@ -1,7 +1,10 @@
-// Tensor-core trunks of AffNet / OriNet / HardNet: first layer (K = 9, fp32 SIMT, fused with the per-patch input
-// normalisation) writing the fp16 canonical layout, then five tcgen05 shifted-window convolutions (tc_conv.cuh).
-// Replaces the conv stacks of architectures.py:207-226 / 36-55 and HardNet.py:67-85 (BatchNorm folded, ReLU fused).
-// Numerics: fp16 operands, fp32 accumulation in TMEM, first layer and heads in fp32 (SURVEY.md §7 hard part 1).
+// Tensor-core engine of AffNet / OriNet / HardNet (replaces the conv stacks and heads of architectures.py:207-235 / 36-82 and
+// HardNet.py:67-101; BatchNorm folded, ReLU fused).  Per net:
+//   tc_first2_kernel    sampler + input_norm + conv1 + conv2 (tc_first.cuh), patches and layer-1 activations stay on the SM
+//   tc_conv_kernel      conv3 .. conv6 as shifted-window implicit GEMMs (tc_conv.cuh)
+//   tc_conv_pair_kernel HardNet conv5 / conv6 on CTA pairs, cta_group::2 (tc_pair.cuh)
+//   tc_head_kernel / tc_headx_kernel   the 8x8 heads as GEMMs over 128-patch tiles (tc_head.cuh)
+// Numerics: fp16 operands with fp16 residual planes where a net needs them, fp32 accumulation in TMEM.
 #include <vector>
 
 #include "net_impl.cuh"
