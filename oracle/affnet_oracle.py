@@ -435,9 +435,16 @@ def get_affine_shape(pyr, resp, LAFs, pyr_idxs, level_idxs, num_features, aff_sd
 
 
 def get_orientation(pyr, LAFs, pyr_idxs, level_idxs, ori_sd, PS=32):
-    """SparseImgRepresenter.py:167-180 (the trailing re-extraction at :178 has no effect on the result)."""
-    patches = extract_patches_from_pyramid(pyr, pyr_idxs, level_idxs, LAFs, PS)
-    R = orinet_forward(patches, ori_sd)
+    """SparseImgRepresenter.py:167-180 (the trailing re-extraction at :178 has no effect on the result).  ori_sd None = the
+    constructor default OriNet=None: OrientationDetector(patch_size=19) on 19x19 patches, angle -> angles2A (LAF.py:180-186)."""
+    if ori_sd is None:
+        patches = extract_patches_from_pyramid(pyr, pyr_idxs, level_idxs, LAFs, 19)
+        ang = orientation_hist(patches)
+        c, s_ = torch.cos(ang).view(-1, 1, 1), torch.sin(ang).view(-1, 1, 1)
+        R = torch.cat([torch.cat([c, s_], dim=2), torch.cat([-s_, c], dim=2)], dim=1)
+    else:
+        patches = extract_patches_from_pyramid(pyr, pyr_idxs, level_idxs, LAFs, PS)
+        R = orinet_forward(patches, ori_sd)
     return torch.cat([torch.bmm(LAFs[:, :, :2], R), LAFs[:, :, 2:]], dim=2), dict(patches=patches, R=R)
 
 
@@ -692,3 +699,35 @@ def lafs_to_ell_t(LAFs):
     ell[:, 0] = LAFs[:, 0, 2]; ell[:, 1] = LAFs[:, 1, 2]
     ell[:, 2] = A[:, 0, 0]; ell[:, 3] = A[:, 0, 1]; ell[:, 4] = A[:, 1, 1]
     return ell
+
+
+def _reproj_distance_matrix(anchor, positive):
+    """distance_matrix_vector of ReprojectionStuff.py:78-86 (NOT the one of Losses.py): returns [len(positive), len(anchor)],
+    sqrt(|d1 + d2 - 2 p a^T + 1e-12|) in fp32."""
+    d1 = torch.sum(anchor * anchor, dim=1)
+    d2 = torch.sum(positive * positive, dim=1)
+    return torch.sqrt(torch.abs((d1.expand(positive.size(0), anchor.size(0)) + torch.t(d2.expand(anchor.size(0), positive.size(0)))
+                                 - 2.0 * torch.mm(positive, torch.t(anchor))) + 1e-12))
+
+
+def gt_correspondences(LAFs1, LAFs2, H1to2, dist_threshold=6.0):
+    """get_GT_correspondence_indexes (ReprojectionStuff.py:126-137, centre part of reprojectLAFs :23-40): centres of LAFs2 are
+    mapped through H1to2^-1 into image 1; because that module's distance matrix comes out transposed, row i is a centre of LAFs1
+    and it counts as a true match when ANY reprojected centre of LAFs2 lies within dist_threshold px of it.
+    Returns (min_dist[mask], index_in_1[mask], index_of_nearest_in_2[mask])."""
+    Hinv = torch.inverse(H1to2.float())
+    c2 = torch.cat([LAFs2[:, :, 2].float(), torch.ones(LAFs2.size(0), 1)], dim=1)          # [n,3]
+    p = c2 @ Hinv.t()
+    p = p[:, :2] / p[:, 2:3]
+    dist = _reproj_distance_matrix(p, LAFs1[:, :, 2].float())
+    mn, idx = torch.min(dist, 1)
+    mask = mn <= dist_threshold
+    return mn[mask], torch.arange(0, idx.size(0))[mask], idx[mask]
+
+
+def match_and_verify(LAFs1, desc1, LAFs2, desc2, H1to2, ratio=0.8, px=6.0):
+    """The reference's application test (train_AffNet_test_on_graffity.py:289-300): SNN matching, then the reprojection check on
+    the tentative pairs.  Returns (n_tentatives, n_true)."""
+    i1, i2, _, _ = match_snn(desc1, desc2, ratio)
+    _, keep, _ = gt_correspondences(LAFs1[i1], LAFs2[i2], H1to2, px)
+    return int(i1.numel()), int(keep.numel())

@@ -16,6 +16,9 @@ changes.  Outputs (all .npz, compressed):
   handcrafted.npz    OrientationDetector / AffineShapeEstimator on 19x19 patches; default detector (OriNet=None) end to end
   ell.npz            LAFs2ellT (the Oxford-affine output of hesaffBaum.py) on the graf crop's final LAFs + synthetic LAFs
                      (`python tests/golden/make_golden.py ell` regenerates only this file from graf_crop.npz)
+  graf_match.npz     the reference's own application test (train_AffNet_test_on_graffity.py:262-300): graf img1 <-> img6, K=3000,
+                     HardNet + SNN 0.8 + 6 px reprojection check, for hand-crafted orientation / OriNet / no orientation:
+                     tentative and true match counts, img6 and H1to6p (`... make_golden.py match`)
 """
 import contextlib
 import io
@@ -182,9 +185,38 @@ def make_ell():
     save("ell.npz", lafs=lafs, ell=ell)
 
 
+def make_match():
+    import importlib
+    m = R.ref_modules()
+    RS, LS = importlib.import_module("ReprojectionStuff"), importlib.import_module("Losses")
+    aff, ori, hn = R.load_nets()
+    rgb1, rgb6 = rgb_of(R.REF + "/test-graf/img1.png"), rgb_of(R.REF + "/test-graf/img6.png")
+    H = np.loadtxt(R.REF + "/test-graf/H1to6p")
+    out = dict(rgb6=rgb6, H1to6=H, K=3000, snn=0.8, px=6.0)
+    for mode in ("hcori", "orinet", "noori"):
+        det = R.make_detector(aff, ori if mode == "orinet" else None, num_features=3000)
+        L1, _, _, d1 = R.run_full(det, hn, gray_of(rgb1), mode != "noori")
+        L2, _, _, d2 = R.run_full(det, hn, gray_of(rgb6), mode != "noori")
+        with torch.no_grad():                                       # train_AffNet_test_on_graffity.py:289-300
+            dm = LS.distance_matrix_vector(d1, d2)
+            mn, i2 = torch.min(dm, 1)
+            dm[:, i2] = 100000
+            sec, _ = torch.min(dm, 1)
+            mask = (mn / (sec + 1e-8)) <= 0.8
+            t1, t2 = torch.arange(0, i2.size(0))[mask].long(), i2[mask].long()
+            _, pi1, _ = RS.get_GT_correspondence_indexes(L1[t1], L2[t2], torch.from_numpy(H).float(), dist_threshold=6)
+        out.update({mode + "_n1": L1.size(0), mode + "_n2": L2.size(0), mode + "_tent": t1.numel(), mode + "_true": pi1.numel(),
+                    mode + "_t1": t1, mode + "_t2": t2})
+        print(mode, L1.size(0), L2.size(0), t1.numel(), "tentatives", pi1.numel(), "true")
+    save("graf_match.npz", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ell":
         make_ell()
+    elif len(sys.argv) > 1 and sys.argv[1] == "match":
+        make_match()
     else:
         main()
         make_ell()
+        make_match()

@@ -448,3 +448,30 @@ def test_lafs2ell_t_8f(L, tmp_path):
     save_ells(str(f), e[ok])
     back = np.loadtxt(str(f))
     assert back.shape == (int(ok.sum()), 5) and np.allclose(back, e[ok].numpy(), rtol=0, atol=1e-9 + 1e-7 * np.abs(e[ok].numpy()).max())
+
+
+@pytest.mark.parametrize("mode", ["orinet", "noori", "hcori"])
+def test_graf_1_to_6_application_counts(L, nets, mode):
+    """The reference's own end-to-end check (train_AffNet_test_on_graffity.py:262-300) through the CUDA path: detect + describe graf
+    img1 and img6 (K=3000), SNN matcher on the device, reprojection check by the oracle.  Counts of the unmodified reference:
+    281/91 (hand-crafted orientation), 309/90 (OriNet), 104/18 (no orientation); a handful of the 6000 keypoints differ (eig-ratio
+    filter at the 1e-3 level), so the counts may move by a few."""
+    from affnet_b200.Losses import match_snn
+    from affnet_b200.SparseImgRepresenter import ScaleSpaceAffinePatchExtractor
+    aff, ori, hn = nets
+    z, f = gold("graf_match.npz"), gold("graf_full.npz")
+    kw = dict(mrSize=5.192, num_features=3000, border=5, num_Baum_iters=1, AffNet=aff)
+    if mode == "orinet":
+        kw["OriNet"] = ori
+    det = ScaleSpaceAffinePatchExtractor(**kw)
+    out = []
+    for rgb in (f["rgb"], z["rgb6"]):
+        dL, _ = det(gray_from_rgb(rgb).to(DEV), do_ori=mode != "noori")
+        out.append((dL, hn(det.extract_patches_from_pyr(dL, PS=32))))
+    (L1, d1), (L2, d2) = out
+    assert L1.size(0) == int(z[mode + "_n1"]) and L2.size(0) == int(z[mode + "_n2"])
+    i1, i2, _, _ = match_snn(d1, d2, float(z["snn"]))
+    _, keep, _ = O.gt_correspondences(L1[i1].cpu(), L2[i2].cpu(), torch.from_numpy(z["H1to6"]), float(z["px"]))
+    tent, true = int(i1.numel()), int(keep.numel())
+    print("\ngraf 1<->6 %s: %d tentatives / %d true (reference %d / %d)" % (mode, tent, true, int(z[mode + "_tent"]), int(z[mode + "_true"])))
+    assert abs(tent - int(z[mode + "_tent"])) <= max(4, 0.03 * int(z[mode + "_tent"])) and abs(true - int(z[mode + "_true"])) <= 4

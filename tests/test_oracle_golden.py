@@ -180,3 +180,18 @@ def test_lafs2ell_t_matches_reference_bit_exactly():
     ok = ~torch.isnan(g).any(dim=1)
     assert torch.equal(e[ok], g[ok])
     assert O.lafs_to_ell_t(torch.zeros(0, 2, 3)).shape == (0, 5)
+
+
+@pytest.mark.parametrize("mode", ["orinet", "noori", "hcori"])
+def test_graf_1_to_6_application_counts(mode):
+    """The reference's own end-to-end check (train_AffNet_test_on_graffity.py:262-300): graf img1 <-> img6, K=3000, HardNet, SNN 0.8,
+    6 px reprojection: tentatives / true matches of the unmodified reference (281/91 hand-crafted orientation, 309/90 OriNet,
+    104/18 none) from the oracle restatement.  The gradient-histogram orientation flips one arg-max bin in 6000 keypoints."""
+    z, f = gold("graf_match.npz"), gold("graf_full.npz")
+    x1, x6 = gray_from_rgb(f["rgb"]), gray_from_rgb(z["rgb6"])
+    ori = W["orinet"] if mode == "orinet" else None
+    L1, _, d1 = O.detect_and_describe(x1, W["affnet"], ori, W["hardnet"], num_features=3000, do_ori=mode != "noori")
+    L2, _, d2 = O.detect_and_describe(x6, W["affnet"], ori, W["hardnet"], num_features=3000, do_ori=mode != "noori")
+    tent, true = O.match_and_verify(L1, d1, L2, d2, torch.from_numpy(z["H1to6"]), float(z["snn"]), float(z["px"]))
+    slack = 2 if mode == "hcori" else 0
+    assert abs(tent - int(z[mode + "_tent"])) <= slack and abs(true - int(z[mode + "_true"])) <= slack, (tent, true)
