@@ -374,15 +374,14 @@ def _main(real_stdout):
         agg = sorted(((sum(v) / prof_steps, len(v) // prof_steps, k) for k, v in per_kernel.items()), reverse=True)
         pk = peaks()
         # dominant kernel family: every tcgen05 kernel of the three CNNs (layers 1+2 fused in tc_first2_kernel, layers 3-6 in
-        # tc_conv_kernel / tc_conv_pair_kernel, HardNet's 8x8 head GEMM in tc_head_kernel); the AffNet / OriNet heads are SIMT
+        # tc_conv_kernel / tc_conv_pair_kernel, the 8x8 head GEMMs in tc_head_kernel / tc_headx_kernel)
         n_aff, n_ori, n_hard = B * int(1.5 * K), n_desc, n_desc
-        TC_FAMILY = ("tc_first2_kernel", "tc_conv_kernel", "tc_conv_pair_kernel", "tc_head_kernel")
-        tc_flop = (n_aff * (FLOP_PER_PATCH["affnet"] - 2 * 3 * 4096) + n_ori * (FLOP_PER_PATCH["orinet"] - 2 * 2 * 9 * 4096)
-                   + n_hard * FLOP_PER_PATCH["hardnet"])
+        TC_FAMILY = ("tc_first2_kernel", "tc_conv_kernel", "tc_conv_pair_kernel", "tc_head_kernel", "tc_headx_kernel")
+        tc_flop = n_aff * FLOP_PER_PATCH["affnet"] + n_ori * FLOP_PER_PATCH["orinet"] + n_hard * FLOP_PER_PATCH["hardnet"]
         tc_ms = sum(t for t, n, k in agg if k in TC_FAMILY)
         tc_launches = sum(n for t, n, k in agg if k in TC_FAMILY)
         ach = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-        roof = {"kernel": "tcgen05 conv kernels (%d launches/step: tc_first2_kernel x3, tc_conv_kernel, tc_conv_pair_kernel, tc_head_kernel; fp16 operands with fp16 "
+        roof = {"kernel": "tcgen05 kernels (%d launches/step: tc_first2_kernel x3, tc_conv_kernel x10, tc_conv_pair_kernel x2, tc_head_kernel, tc_headx_kernel x2; fp16 operands with fp16 "
                           "residual planes for AffNet/OriNet, fp32 accumulate in TMEM)" % tc_launches,
                 "bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"],
                 "traffic": ncu_traffic(B), "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)", "kernel_ms_per_step": tc_ms,
