@@ -12,8 +12,14 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     path = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "bench_final.json")
-    d = json.loads(open(path).read().strip().splitlines()[-1])
-    json.dump(d, open(os.path.join(ROOT, "profiles", tag + "_bench_latest.json"), "w"), indent=1)
+    txt = open(path).read().strip()
+    try:
+        d = json.loads(txt)                       # an already stored (indented) bench line
+    except json.JSONDecodeError:
+        d = json.loads(txt.splitlines()[-1])      # raw bench.py output: the JSON line is the last one
+    dst = os.path.join(ROOT, "profiles", tag + "_bench_latest.json")
+    if os.path.abspath(path) != os.path.abspath(dst):
+        json.dump(d, open(dst, "w"), indent=1)
     r = d["roofline"]
     md = ["# %s: one step, kernel by kernel (CUDA events after every launch, `bench.py`)" % tag, "",
           "Workload: %s.  Device-resident %.1f Mpix/s (%.2f ms/step), end to end %.1f Mpix/s; clocks %s." % (
