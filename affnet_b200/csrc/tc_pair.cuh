@@ -31,6 +31,18 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
     asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(bar)));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// Accumulator hand-over (tempty): carries no data, only "these TMEM columns were read", which tcgen05.fence::before_thread_sync
+// orders.  The release form above makes the epilogue warp wait for its global stores first (20-30 % membar stall samples in ncu);
+// the relaxed form is the prepared experiment for the next round (build with AG_EXTRA_FLAGS=-DAG_PAIR_RELAXED_ARRIVE).
+__device__ __forceinline__ void mbar_arrive_leader_nodata(uint64_t* bar) {
+#ifdef AG_PAIR_RELAXED_ARRIVE
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(bar)));
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#else
+    mbar_arrive_leader(bar);
+#endif
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n .reg .pred P;\n WAIT_%=:\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%0], %1;\n @P bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(
@@ -217,7 +229,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1) tc_conv_pair
                 if (c0 + 32 >= COUT) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&tempty[ab]);
+                    if (lane == 0) mbar_arrive_leader_nodata(&tempty[ab]);
                 }
                 if (ok) {
 #pragma unroll
