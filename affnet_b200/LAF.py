@@ -67,15 +67,19 @@ def get_LAFs_scales(LAFs):
 
 
 def LAFs2ell(in_LAFs):
-    """LAF.py:225-240: [n,2,3] numpy LAFs -> [x y a b c] ellipse rows (float64 numpy, host-side output format)."""
-    LAFs = np.asarray(in_LAFs, dtype=np.float64).reshape(-1, 2, 3)
+    """LAF.py:225-240: [n,2,3] numpy LAFs -> [x y a b c] ellipse rows (host-side output format).  As in the reference the SVD runs
+    in the dtype of the input (float32 for `LAFs.cpu().numpy()`, hesaffnet.py:56) and the rows are returned as float64."""
+    LAFs = np.asarray(in_LAFs)
+    if not np.issubdtype(LAFs.dtype, np.floating):
+        LAFs = LAFs.astype(np.float64)
+    LAFs = LAFs.reshape(-1, 2, 3)
     ell = np.zeros((len(LAFs), 5))
     for i in range(len(LAFs)):
         A = LAFs[i, :, :2]
         scale = np.sqrt(A[0, 0] * A[1, 1] - A[0, 1] * A[1, 0] + 1e-10)
         u, W, _ = np.linalg.svd(A / scale, full_matrices=True)
         W = 1.0 / (W * W * scale * scale)
-        M = u @ np.diag(W) @ u.T
+        M = np.matmul(np.matmul(u, np.diag(W)), u.transpose())
         ell[i] = [LAFs[i, 0, 2], LAFs[i, 1, 2], M[0, 0], M[0, 1], M[1, 1]]
     return ell
 

@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(NT) blur_kernel(const float* __restrict__ in, 
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const float* img = in + (size_t)b * h * w;
     // 1. input window with replicate (clamp) addressing
-#ifdef AG_BLUR_VEC_FILL
-    // prepared experiment (next round; build with AG_EXTRA_FLAGS=-DAG_BLUR_VEC_FILL): interior tiles fill the window with 128-bit loads
-    // (the scalar fill is 30 % of this kernel's stall samples); same values in the same places, so the arithmetic does not change
+#ifndef AG_BLUR_SCALAR_FILL
+    // interior tiles fill the window with 128-bit loads (the scalar fill was 30 % of this kernel's stall samples); same values in
+    // the same places, so the arithmetic does not change
     if ((w & 3) == 0 && x0 - R4 >= 0 && x0 - R4 + G::IW <= w && (reinterpret_cast<size_t>(img) & 15) == 0) {
         constexpr int QW = G::IW / 4;
         static_assert(G::IW % 4 == 0, "window rows are whole float4s");

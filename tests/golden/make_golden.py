@@ -182,7 +182,11 @@ def make_ell():
     lafs = torch.cat([torch.from_numpy(z["ori_dLAFs"]), torch.from_numpy(z["noori_dLAFs"]), syn]).float()
     with torch.no_grad():
         ell = m["LAF"].LAFs2ellT(lafs)
-    save("ell.npz", lafs=lafs, ell=ell)
+    # host-side output format (LAF.py:225-240, numpy float64 SVD) on the rows it is defined for (positive determinant)
+    ln = lafs.numpy()
+    pos = (ln[:, 0, 0] * ln[:, 1, 1] - ln[:, 0, 1] * ln[:, 1, 0]) > 0
+    ell_host = m["LAF"].LAFs2ell(ln[pos])
+    save("ell.npz", lafs=lafs, ell=ell, host_rows=np.nonzero(pos)[0], ell_host=ell_host)
 
 
 def make_match():

@@ -48,3 +48,26 @@ def match_keypoints(LA, LB, tol_px=0.05):
         return np.zeros(0, int), np.zeros(0, int)
     k = np.array(keep)
     return k[:, 0], k[:, 1]
+
+
+def laf_rel_errors(LA, LB):
+    """Parity contract for matched LAFs (SURVEY Q7 ii, north_star 1e-3): errors RELATIVE to the LAF scale s = sqrt(|det A|) of the
+    first argument.  Returns (max |dA| / s, max |dcentre| / s) over the rows."""
+    A, B = LA.double(), LB.double()
+    s = (A[:, 0, 0] * A[:, 1, 1] - A[:, 0, 1] * A[:, 1, 0]).abs().sqrt().clamp_min(1e-12)
+    eA = ((A[:, :, :2] - B[:, :, :2]).abs().amax(dim=(1, 2)) / s).max().item()
+    ec = ((A[:, :, 2] - B[:, :, 2]).abs().amax(dim=1) / s).max().item()
+    return eA, ec
+
+
+def parity_report(oL, odesc, dL, desc, tag=""):
+    """Match keypoints of the oracle (oL, odesc) and the CUDA path (dL, desc); returns dict(matched, n, eA, ec, dd) and prints it."""
+    ia, ib = match_keypoints(oL, dL)
+    eA, ec = laf_rel_errors(oL[ia], dL[ib]) if len(ia) else (float("inf"), float("inf"))
+    dd = (odesc[ia] - desc[ib]).abs().max().item() if len(ia) else float("inf")
+    out = dict(matched=len(ia), n=int(oL.shape[0]), n_ours=int(dL.shape[0]), eA=eA, ec=ec, dd=dd)
+    print("\n%s: matched %d/%d (ours %d)  max|dA|/scale %.2e  max|dcentre|/scale %.2e  max|ddesc| %.2e" % (tag, out["matched"], out["n"], out["n_ours"], eA, ec, dd))
+    return out
+
+
+TOL = 1e-3     # north_star: LAF parameters (relative to the LAF scale) and HardNet descriptors within 1e-3

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import affnet_oracle as O
-from helpers import gold, gray_from_rgb, load_weights, match_keypoints
+from helpers import TOL, gold, gray_from_rgb, laf_rel_errors, load_weights, match_keypoints, parity_report
 
 pytestmark = pytest.mark.gpu
 
@@ -304,17 +304,15 @@ def test_end_to_end_vs_oracle(L, nets, name, K, do_ori):
     # >= 99.5 %; the near-isotropic eigen-discriminant test of batch_eig2x2 flips ~1e-3 of the candidates under
     # any fp32 perturbation (the oracle itself differs from the reference by 2/3000 there), so allow 3 at small K
     assert len(ia) >= oL.shape[0] - max(3, 0.005 * oL.shape[0]), (len(ia), oL.shape[0])
-    dl = (oL[ia] - dL.cpu()[ib]).abs().max().item()
-    dd = (odesc[ia] - desc.cpu()[ib]).abs().max().item()
-    print("\n%s K=%d ori=%s: matched %d/%d  max|dLAF| %.2e px  max|ddesc| %.2e" % (name, K, do_ori, len(ia), oL.shape[0], dl, dd))
-    assert dl < 5e-2 and dd < 5e-3
+    rep = parity_report(oL, odesc, dL.cpu(), desc.cpu(), "%s K=%d ori=%s vs oracle" % (name, K, do_ori))
+    assert rep["eA"] < TOL and rep["ec"] < TOL and rep["dd"] < TOL, rep
     # the reference's own golden output, same contract
     z = gold(name)
     tag = "ori" if do_ori else "noori"
     gL = torch.from_numpy(z[tag + "_dLAFs"])
-    ia, ib = match_keypoints(gL, dL.cpu())
-    assert len(ia) >= gL.shape[0] - max(3, 0.005 * gL.shape[0])
-    assert (torch.from_numpy(z[tag + "_desc"]).float()[ia] - desc.cpu()[ib]).abs().max() < 5e-3
+    rep = parity_report(gL, torch.from_numpy(z[tag + "_desc"]).float(), dL.cpu(), desc.cpu(), "%s K=%d ori=%s vs reference golden" % (name, K, do_ori))
+    assert rep["matched"] >= gL.shape[0] - max(3, 0.005 * gL.shape[0])
+    assert rep["eA"] < TOL and rep["ec"] < TOL and rep["dd"] < TOL, rep
 
 
 def test_pipeline_batched_equals_single_image_api(L, nets):
@@ -373,9 +371,43 @@ def test_full_size_properties(L, nets):
     oL, oresp, st = O.detect(imgs[0:1].cpu(), W["affnet"], W["orinet"], K, do_ori=True)
     odesc, _, _ = O.describe(oL, st, W["hardnet"])
     n = int(cnt[0])
-    ia, ib = match_keypoints(oL, lafs[0, :n].cpu())
-    assert len(ia) >= 0.995 * oL.shape[0]
-    assert (odesc[ia] - desc[0, :n].cpu()[ib]).abs().max() < 5e-3
+    rep = parity_report(oL, odesc, lafs[0, :n].cpu(), desc[0, :n].cpu(), "synthetic 1024x768 K=2000 (bench workload) vs oracle")
+    assert rep["matched"] >= 0.995 * oL.shape[0]
+    assert rep["eA"] < TOL and rep["ec"] < TOL and rep["dd"] < TOL, rep
+
+
+def _graf_1024():
+    """SURVEY 8(d) input 2: graf img1 (800x640) resized to 1024x768 with cv2 INTER_LINEAR, then the channel mean of hesaffnet.py:35-39."""
+    import cv2
+    rgb = cv2.resize(gold("graf_full.npz")["rgb"], (1024, 768), interpolation=cv2.INTER_LINEAR)
+    return gray_from_rgb(rgb)
+
+
+@pytest.mark.parametrize("cfg", ["graf1024", "1080p", "4k"])
+def test_benchmark_configs_vs_oracle(L, nets, cfg):
+    """The configurations bench.py measures (BASELINE.json configs 2, 3, 5), one image each through the batched pipeline, against the
+    oracle on the same image: >= 99.5 % of the keypoints matched, matched LAFs (relative to their scale) and descriptors within 1e-3."""
+    from affnet_b200.pipeline import DetectDescribePipeline
+    aff, ori, hn = nets
+    if cfg == "graf1024":
+        img, K, border = _graf_1024(), 2000, 5
+    elif cfg == "1080p":
+        img, K, border = O.synthetic_image(1080, 1920, 1234), 4000, 5
+    else:
+        img, K, border = O.synthetic_image(2160, 3840, 4321), 8000, 33          # border=33 -> the 5-octave pyramid of config 5
+    H, Wd = img.shape[2:]
+    pipe = DetectDescribePipeline(1, H, Wd, aff, hn, ori, num_features=K, border=border, do_ori=True)
+    lafs, resp, desc, cnt = pipe.run(img.to(DEV))
+    pipe.check()
+    n = int(cnt[0])
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    oL, oresp, st = O.detect(img, W["affnet"], W["orinet"], K, border=border, do_ori=True)
+    odesc, _, _ = O.describe(oL, st, W["hardnet"])
+    if cfg == "4k":
+        assert len(st["pyr"]) == 5
+    rep = parity_report(oL, odesc, lafs[0, :n].cpu(), desc[0, :n].cpu(), "%s K=%d border=%d vs oracle" % (cfg, K, border))
+    assert abs(n - oL.shape[0]) <= 0.005 * K and rep["matched"] >= 0.995 * oL.shape[0], rep
+    assert rep["eA"] < TOL and rep["ec"] < TOL and rep["dd"] < TOL, rep
 
 
 def test_handcrafted_estimators_8f(L):

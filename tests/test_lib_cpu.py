@@ -111,3 +111,19 @@ def test_modules_keep_reference_interface(L):
     assert d.num == -1 and d.th == -1                               # SparseImgRepresenter.py:33-37
     for m in ("forward", "multiScaleDetector", "getAffineShape", "getOrientation", "extract_patches_from_pyr"):
         assert callable(getattr(d, m))
+
+
+def test_host_lafs2ell_matches_reference_golden():
+    """a17: the host-side output format LAFs2ell (LAF.py:225-240, float64 numpy SVD) against rows produced by the unmodified
+    reference (tests/golden/make_golden.py::make_ell), plus the text file layout of hesaffnet.py:56-60."""
+    import numpy as np
+    from helpers import gold
+    from affnet_b200.LAF import LAFs2ell
+    z = gold("ell.npz")
+    lafs = z["lafs"][z["host_rows"]]
+    e = LAFs2ell(lafs)
+    g = z["ell_host"]
+    assert e.shape == g.shape == (len(lafs), 5) and e.dtype == np.float64
+    assert np.array_equal(e[:, :2], g[:, :2])
+    assert np.allclose(e[:, 2:], g[:, 2:], rtol=1e-6, atol=0)       # same float32 SVD as the reference (LAPACK build may differ in the last bit)
+    assert LAFs2ell(np.zeros((0, 2, 3))).shape == (0, 5)
