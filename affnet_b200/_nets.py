@@ -60,8 +60,8 @@ class _NativeNet(nn.Module):
         return self._handle
 
     def set_engine(self, engine):
-        """engine: L.ENGINE_SIMT (exact fp32 CUDA cores), L.ENGINE_TC (tcgen05, default) or L.ENGINE_TC_EXACT (AffNet / OriNet:
-        residual planes everywhere + fp32 heads); see include/affnet_b200.h."""
+        """engine: L.ENGINE_SIMT (exact fp32 CUDA cores), L.ENGINE_TC (tcgen05, default), L.ENGINE_TC_EXACT (AffNet / OriNet: fp32
+        heads on top of the residual-plane trunk) or L.ENGINE_TC_FAST (AffNet without activation residuals); see include/affnet_b200.h."""
         self._engine = engine
         if self._handle is not None:
             L.check(L.lib().ag_net_set_engine(self._handle, engine))

@@ -404,6 +404,14 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
                                 dst[(((((size_t)sp * 9 + tap) * kc + g) * (1 + sw) + part) * nt + nn) * 8 + e] = val;
                             }
     }
+    // second-generation packs (tcx_pack_layer): kernel-row blocks with the three taps stacked along N
+    std::vector<__half> packed_x;
+    size_t wx_off[6] = {0, 0, 0, 0, 0, 0};
+    for (int l = 1; l < 6; l++) {
+        wx_off[l] = packed_x.size();
+        tcx_pack_layer(packed.data() + w_off[l], cfg[l].cin, cfg[l].cout, tcx_stride(l), tcx_nsplit(kind, l), tcx_split_w(kind, l), w_scale[l], packed_x);
+        while (packed_x.size() % 8) packed_x.push_back(__float2half_rn(0.f));
+    }
     size_t headh_off = 0;
     float head_scale = 1.0f;
     if (kind == AG_NET_HARDNET) {
@@ -443,7 +451,7 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
     ag_net* net = new ag_net();
     memset(net, 0, sizeof(*net));
     net->kind = kind;
-    net->engine = AG_ENGINE_TC;
+    net->engine = AG_ENGINE_TC2;   // second-generation tensor-core engine (nets_tcx.cu); AG_ENGINE_TC selects the first generation
     net->head_inv_scale = 1.0f / head_scale;
     for (int l = 0; l < 6; l++) net->w_inv_scale[l] = 1.0f / w_scale[l];
     {
@@ -453,11 +461,15 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
         if (rch != AG_OK) { cudaFree(net->d_all_h); delete net; return rch; }
         for (int l = 1; l < 6; l++) net->d_wh[l] = net->d_all_h + wh_off[l];
         net->d_headh = net->d_all_h + headh_off;
+        rch = check_cuda(cudaMalloc(&net->d_all_x, packed_x.size() * sizeof(__half)), "cudaMalloc fp16 weights (second generation)");
+        if (rch == AG_OK) rch = check_cuda(cudaMemcpy(net->d_all_x, packed_x.data(), packed_x.size() * sizeof(__half), cudaMemcpyHostToDevice), "upload fp16 weights");
+        if (rch != AG_OK) { cudaFree(net->d_all_h); cudaFree(net->d_all_x); delete net; return rch; }
+        for (int l = 1; l < 6; l++) net->d_wx[l] = net->d_all_x + wx_off[l];
     }
     int rc = check_cuda(cudaMalloc(&net->d_all, packed.size() * sizeof(float)), "cudaMalloc weights");
-    if (rc != AG_OK) { cudaFree(net->d_all_h); delete net; return rc; }
+    if (rc != AG_OK) { cudaFree(net->d_all_h); cudaFree(net->d_all_x); delete net; return rc; }
     rc = check_cuda(cudaMemcpy(net->d_all, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice), "upload weights");
-    if (rc != AG_OK) { cudaFree(net->d_all); cudaFree(net->d_all_h); delete net; return rc; }
+    if (rc != AG_OK) { cudaFree(net->d_all); cudaFree(net->d_all_h); cudaFree(net->d_all_x); delete net; return rc; }
     for (int l = 0; l < 6; l++) { net->d_w[l] = net->d_all + w_off[l]; net->d_b[l] = net->d_all + b_off[l]; }
     net->d_w1 = net->d_w[0];
     net->d_head_w = net->d_all + hw_off;
@@ -470,12 +482,14 @@ void ag_net_destroy(ag_net_t* net) {
     if (!net) return;
     cudaFree(net->d_all);
     cudaFree(net->d_all_h);
+    cudaFree(net->d_all_x);
     delete net;
 }
 
 int ag_net_set_engine(ag_net_t* net, int engine) {
     AG_REQUIRE(net != nullptr, "NULL net");
-    AG_REQUIRE(engine == AG_ENGINE_SIMT || engine == AG_ENGINE_TC || engine == AG_ENGINE_TC_EXACT, "unknown engine");
+    AG_REQUIRE(engine == AG_ENGINE_SIMT || engine == AG_ENGINE_TC || engine == AG_ENGINE_TC_EXACT || engine == AG_ENGINE_TC_FAST || engine == AG_ENGINE_TC2, "unknown engine");
+    AG_REQUIRE(engine != AG_ENGINE_TC_FAST || net->kind == AG_NET_AFFNET, "the fast tensor-core engine exists for AffNet only");
     AG_REQUIRE(engine != AG_ENGINE_TC_EXACT || net->kind != AG_NET_HARDNET, "the exact tensor-core engine exists for AffNet / OriNet");
     net->engine = engine;
     return AG_OK;
@@ -489,7 +503,8 @@ size_t ag_net_workspace_bytes(int kind, int n) {
     const size_t simt = 2 * align_up((size_t)n * per * sizeof(float), 256);
     // tensor-core engine: two fp16 ping-pong buffers + the hi/lo fp16 head operand (AffNet/OriNet, whole 128-patch tiles) or the fp16 head operand (HardNet, padded
     // to a multiple of 128 patches)
-    const size_t tcb = 2 * align_up((size_t)n * tc_act_bytes(kind == AG_NET_AFFNET ? AG_NET_ORINET : kind), 256) +
+    const size_t act1 = (size_t)n * tc_act_bytes(kind == AG_NET_AFFNET ? AG_NET_ORINET : kind), act2 = tcx_act_bytes(n);   // first / second generation
+    const size_t tcb = 2 * align_up(act1 > act2 ? act1 : act2, 256) +
                        (kind == AG_NET_HARDNET ? align_up(((size_t)n + 128) * 8192 * 2, 256) : align_up(tc_headx_bytes(n), 256));
     return simt > tcb ? simt : tcb;
 }
@@ -531,7 +546,8 @@ static int run_trunk(const ag_net* net, const float* patches, const tc::FirstSrc
         // the workspace [a, a + 2*(b-a)) is re-carved as [bufA | bufB | head-GEMM operand]
         char* base = (char*)a;
         const size_t total = 2 * (size_t)((char*)b - (char*)a);
-        const size_t act = align_up((size_t)n * tc_act_bytes(net->engine == AG_ENGINE_TC_EXACT ? AG_NET_ORINET : net->kind), 256);
+        const size_t act = net->engine == AG_ENGINE_TC2 ? align_up(tcx_act_bytes(n), 256)
+                                                        : align_up((size_t)n * tc_act_bytes(net->engine == AG_ENGINE_TC_FAST ? net->kind : AG_NET_ORINET), 256);
         const size_t fbytes = tc_headx_bytes(n);
         if (2 * act + fbytes > total) { set_error("tensor-core workspace too small"); return AG_ERR_CAPACITY; }
         void* bufA = base;
@@ -539,7 +555,8 @@ static int run_trunk(const ag_net* net, const float* patches, const tc::FirstSrc
         b = (float*)(base + 2 * act);
         *feat = b;
         if (net->kind == AG_NET_HARDNET) { set_error("HardNet tensor-core path has its own entry"); return AG_ERR_INVALID; }
-        if (net->kind == AG_NET_ORINET || net->engine == AG_ENGINE_TC_EXACT) return tc_trunk_orinet(net, src, n, group, count, bufA, bufB, b, st);
+        if (net->engine == AG_ENGINE_TC2) return tcx_trunk_affori(net, src, n, group, count, bufA, bufB, b, st, 6);
+        if (net->engine != AG_ENGINE_TC_FAST) return tc_trunk_orinet(net, src, n, group, count, bufA, bufB, b, st);   // residual planes of weights and activations
         return tc_trunk_affnet(net, src, n, group, count, bufA, bufB, b, st);
     }
     *feat = b;
@@ -574,7 +591,7 @@ static int affnet_impl(const ag_net_t* net, const float* d_patches, const tc::Fi
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = run_trunk(net, d_patches, src, n, group, d_count, a, b, &b, st))) return rc;
-    if (net->engine == AG_ENGINE_TC) return tc_headx_forward(net, b, n, group, d_count, d_out, nullptr, st);
+    if (net->engine == AG_ENGINE_TC || net->engine == AG_ENGINE_TC_FAST || net->engine == AG_ENGINE_TC2) return tc_headx_forward(net, b, n, group, d_count, d_out, nullptr, st);
     affnet_head_kernel<<<cdiv(n, 8), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, n, group, d_count);
     AG_CHECK_LAUNCH("affnet_head_kernel");
     return AG_OK;
@@ -591,7 +608,7 @@ static int orinet_impl(const ag_net_t* net, const float* d_patches, const tc::Fi
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = run_trunk(net, d_patches, src, n, group, d_count, a, b, &b, st))) return rc;
-    if (net->engine == AG_ENGINE_TC) return tc_headx_forward(net, b, n, group, d_count, d_out, d_angle, st);
+    if (net->engine == AG_ENGINE_TC || net->engine == AG_ENGINE_TC2) return tc_headx_forward(net, b, n, group, d_count, d_out, d_angle, st);
     orinet_head_kernel<<<cdiv(n, OH_W * OH_P), OH_W * 32, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, d_angle, n, group, d_count);
     AG_CHECK_LAUNCH("orinet_head_kernel");
     return AG_OK;
@@ -607,6 +624,13 @@ static int hardnet_impl(const ag_net_t* net, const float* d_patches, const tc::F
     int rc = split_ws(net->kind, n, d_ws, ws_bytes, &a, &b);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (net->engine == AG_ENGINE_TC2) {
+        char* base = (char*)d_ws;
+        const size_t act = align_up(tcx_act_bytes(n), 256);
+        const tc::FirstSrc s0 = src ? *src : tc_src_patches(d_patches);
+        if ((rc = tcx_trunk_hardnet(net, s0, n, group, d_count, base, base + act, base + 2 * act, st, 6))) return rc;
+        return tc_hardnet_head(net, base + 2 * act, n, group, d_count, d_out, st);
+    }
     if (net->engine == AG_ENGINE_TC) {
         char* base = (char*)d_ws;
         const size_t act = align_up((size_t)n * tc_act_bytes(net->kind), 256);

@@ -156,9 +156,15 @@ int tc_hardnet_forward(const ag_net* net, const tc::FirstSrc& src0, int n, int g
         if ((rc = launch_pair<64, 128, 16, 2, 3, PLAIN>(B, A, net->d_wh[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
         if ((rc = launch_pair<128, 128, 8, 1, 2, HEADL>(A, headbuf, net->d_wh[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st))) return rc;
     }
+    return tc_hardnet_head(net, headbuf, n, group, count, out, st);
+}
+
+// HardNet 8x8 head GEMM + BatchNorm + L2 norm over the head operand a trunk left in `headbuf`
+int tc_hardnet_head(const ag_net* net, const void* headbuf, int n, int group, const int* count, float* out, cudaStream_t st) {
+    using namespace tc;
     static bool configured = false;
     if (!configured) {
-        rc = check_cuda(cudaFuncSetAttribute(tc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM), "tc_head smem attr");
+        int rc = check_cuda(cudaFuncSetAttribute(tc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM), "tc_head smem attr");
         if (rc != AG_OK) return rc;
         configured = true;
     }

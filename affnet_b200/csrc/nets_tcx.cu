@@ -1,0 +1,203 @@
+// Second-generation tensor-core engine of AffNet / OriNet / HardNet (tcx_first.cuh, tcx_conv.cuh): row tiles without x padding, the
+// three taps of a kernel row stacked along N, x shifts by warp shuffles in the epilogue.  Replaces the conv stacks of
+// architectures.py:207-235 / 36-82 and HardNet.py:67-101 (BatchNorm folded, ReLU fused); the 8x8 heads stay the GEMM kernels of
+// tc_head.cuh (same head-operand layout).  Per net:  tcx_first_kernel (sampler + input_norm + conv1 + conv2)  ->  tcx_conv_kernel x4.
+// Numerics: AffNet / OriNet with fp16 residual planes of weights and activations in every layer (three MMAs per K step, fp32-grade);
+// HardNet fp16 activations, weights with their fp16 residual in layers 2-4 (measured in emulation on the 2000 graf patches: the
+// descriptor error of plain fp16 weights is 1.1e-3, dominated by the weight rounding of layers 2-4; with their residuals 4e-4).
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "net_impl.cuh"
+#include "tcx_conv.cuh"
+#include "tcx_first.cuh"
+
+namespace ag {
+namespace tcx {
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+static int ensure_smem_attr(const void* func, int bytes, bool* configured, const char* what) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (configured[dev]) return AG_OK;
+    int rc = check_cuda(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), what);
+    if (rc == AG_OK) configured[dev] = true;
+    return rc;
+}
+
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW>
+static int launch_conv(const void* in, void* out, const __half* w, const float* b, float inv_scale, int n, int group, const int* count, cudaStream_t st) {
+    using Cfg = XCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW>;
+    auto kern = tcx_conv_kernel<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW>;
+    static bool configured[64] = {};   // per device (the attribute is per device)
+    int rc = ensure_smem_attr((const void*)kern, (int)Cfg::SMEM, configured, "tcx_conv smem attr");
+    if (rc != AG_OK) return rc;
+    XArgs a;
+    a.in = (const __half*)in; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.n = n; a.group = group; a.count = count;
+    const int units = Cfg::In::PAIR ? (n + 1) / 2 : n;
+    int gx = num_sms() / NSPLIT;
+    if (gx > units) gx = units;
+    if (gx < 1) gx = 1;
+    kern<<<dim3(gx, NSPLIT), Cfg::THREADS, Cfg::SMEM, st>>>(a);
+    AG_CHECK_LAUNCH("tcx_conv_kernel");
+    return AG_OK;
+}
+
+template <int C1, int COUT, int SA, int SW, int OSA>
+static int launch_first(void* out, const __half* w, const float* b, float inv_scale, int n, int group, const int* count, cudaStream_t st, const FirstSrc& src) {
+    using Cfg = XFirstCfg<C1, COUT, SA, SW, OSA>;
+    auto kern = tcx_first_kernel<C1, COUT, SA, SW, OSA>;
+    static bool configured[64] = {};
+    int rc = ensure_smem_attr((const void*)kern, (int)Cfg::SMEM, configured, "tcx_first smem attr");
+    if (rc != AG_OK) return rc;
+    XArgs a;
+    a.in = nullptr; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.n = n; a.group = group; a.count = count;
+    int gx = num_sms();
+    if (gx > n) gx = n;
+    if (gx < 1) gx = 1;
+    kern<<<gx, Cfg::THREADS, Cfg::SMEM, st>>>(a, src);
+    AG_CHECK_LAUNCH("tcx_first_kernel");
+    return AG_OK;
+}
+
+// debug / test helper: an activation buffer in one of the HBM layouts -> fp32 [n][C][H][H] (hi + lo planes added)
+__global__ void tcx_decode_kernel(const __half* __restrict__ buf, int layout, int C, int osa, int H, int n, float* __restrict__ out) {
+    const size_t total = (size_t)n * C * H * H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % H), y = (int)((i / H) % H), c = (int)((i / ((size_t)H * H)) % C), pi = (int)(i / ((size_t)H * H * C));
+        const int slots = layout_slots(layout), groups = (C / 8) * (1 + osa);
+        const int unit = layout_pair(layout) ? (pi >> 1) : pi;
+        const int slot = layout_slot(layout, y, x, pi & 1);
+        const __half* ub = buf + (size_t)unit * groups * slots * 8;
+        float v = __half2float(ub[((size_t)(c / 8) * slots + slot) * 8 + (c & 7)]);
+        if (osa) v += __half2float(ub[((size_t)(C / 8 + c / 8) * slots + slot) * 8 + (c & 7)]);
+        out[i] = v;
+    }
+}
+
+}  // namespace tcx
+
+// ---- weight packing (host) --------------------------------------------------------------------------------------------------------
+// wf: fp32 [tap = dy*3+dx][ci][co] (BatchNorm folded), scale: power of two.  Blocks per (split, dy, 16 input channels):
+//   stride 1: [K group (2)][part hi|lo][dx 0,1,2][co][8]
+//   stride 2: odd-x plane [K group][part][dx 0,2][co][8], then even-x plane [K group][part][dx 1][co][8]
+void tcx_pack_layer(const float* wf, int ci, int co, int stride, int nsplit, int sw, float scale, std::vector<__half>& out) {
+    const int nt = co / nsplit;
+    auto put = [&](int dy, int dx, int cin, int c, int part) {
+        const float v = scale * wf[((size_t)(dy * 3 + dx) * ci + cin) * co + c];
+        const __half hi = __float2half_rn(v);
+        out.push_back(part == 0 ? hi : __float2half_rn(v - __half2float(hi)));
+    };
+    for (int sp = 0; sp < nsplit; sp++)
+        for (int dy = 0; dy < 3; dy++)
+            for (int j = 0; j < ci / 16; j++) {
+                if (stride == 1) {
+                    for (int kg = 0; kg < 2; kg++)
+                        for (int part = 0; part <= sw; part++)
+                            for (int dx = 0; dx < 3; dx++)
+                                for (int c = 0; c < nt; c++)
+                                    for (int e = 0; e < 8; e++) put(dy, dx, (2 * j + kg) * 8 + e, sp * nt + c, part);
+                } else {
+                    for (int kg = 0; kg < 2; kg++)
+                        for (int part = 0; part <= sw; part++)
+                            for (int dx = 0; dx < 3; dx += 2)
+                                for (int c = 0; c < nt; c++)
+                                    for (int e = 0; e < 8; e++) put(dy, dx, (2 * j + kg) * 8 + e, sp * nt + c, part);
+                    for (int kg = 0; kg < 2; kg++)
+                        for (int part = 0; part <= sw; part++)
+                            for (int c = 0; c < nt; c++)
+                                for (int e = 0; e < 8; e++) put(dy, 1, (2 * j + kg) * 8 + e, sp * nt + c, part);
+                }
+            }
+}
+
+int tcx_nsplit(int kind, int layer) { return (kind == AG_NET_HARDNET && layer >= 4) ? 2 : 1; }
+// weight residual copies: AffNet / OriNet every layer; HardNet layers 2-4 (layer index 1..3)
+int tcx_split_w(int kind, int layer) { return kind == AG_NET_HARDNET ? (layer <= 3 ? 1 : 0) : 1; }
+int tcx_stride(int layer) { return (layer == 2 || layer == 4) ? 2 : 1; }
+
+// bytes of each of the two ping-pong activation buffers for n patches (largest layer output: 64 KiB per patch; pair layouts round n up)
+size_t tcx_act_bytes(int n) { return (size_t)(n + 1) * 65536; }
+
+// ---- trunks -------------------------------------------------------------------------------------------------------------------------
+// AffNet / OriNet (same shapes, own weights): features as fp16 hi + lo planes in the head-GEMM layout.  upto: stop after conv layer
+// `upto` (2..6; for the debug decode), 6 = whole trunk.
+int tcx_trunk_affori(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, void* feat,
+                     cudaStream_t st, int upto) {
+    using namespace tcx;
+    tc::FirstSrc src = src0;
+    src.w1 = net->d_w1; src.b1 = net->d_b[0]; src.w1_inv = net->w_inv_scale[0]; src.w1_scale = 1.0f / net->w_inv_scale[0];
+    int rc;
+    if ((rc = launch_first<16, 16, 1, 1, 1>(bufB, net->d_wx[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src))) return rc;
+    if (upto <= 2) return AG_OK;
+    if ((rc = launch_conv<16, 32, 32, 2, 1, 3, L_S1_16, 1, 1, 1, 4>(bufB, bufA, net->d_wx[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
+    if (upto <= 3) return AG_OK;
+    if ((rc = launch_conv<32, 32, 16, 1, 1, 4, L_S2_8P, 1, 1, 1, 4>(bufA, bufB, net->d_wx[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
+    if (upto <= 4) return AG_OK;
+    if ((rc = launch_conv<32, 64, 16, 2, 1, 2, L_S1_8P, 1, 1, 1, 8>(bufB, bufA, net->d_wx[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
+    if (upto <= 5) return AG_OK;
+    return launch_conv<64, 64, 8, 1, 1, 2, L_HEAD, 1, 1, 1, 8>(bufA, feat, net->d_wx[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st);
+}
+
+int tcx_trunk_hardnet(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, void* headbuf,
+                      cudaStream_t st, int upto) {
+    using namespace tcx;
+    tc::FirstSrc src = src0;
+    src.w1 = net->d_w1; src.b1 = net->d_b[0]; src.w1_inv = net->w_inv_scale[0]; src.w1_scale = 1.0f / net->w_inv_scale[0];
+    int rc;
+    if ((rc = launch_first<32, 32, 0, 1, 0>(bufB, net->d_wx[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src))) return rc;
+    if (upto <= 2) return AG_OK;
+    if ((rc = launch_conv<32, 64, 32, 2, 1, 2, L_S1_16, 0, 1, 0, 8>(bufB, bufA, net->d_wx[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
+    if (upto <= 3) return AG_OK;
+    if ((rc = launch_conv<64, 64, 16, 1, 1, 2, L_S2_8P, 0, 1, 0, 8>(bufA, bufB, net->d_wx[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
+    if (upto <= 4) return AG_OK;
+    if ((rc = launch_conv<64, 128, 16, 2, 2, 2, L_S1_8P, 0, 0, 0, 8>(bufB, bufA, net->d_wx[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
+    if (upto <= 5) return AG_OK;
+    return launch_conv<128, 128, 8, 1, 2, 2, L_HEAD, 0, 0, 0, 8>(bufA, headbuf, net->d_wx[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st);
+}
+
+}  // namespace ag
+
+using namespace ag;
+
+extern "C" {
+
+// Developer diagnostic (tests/test_gpu_tcx.py): run the second-generation trunk of `net` on materialised patches [n,32,32] up to conv
+// layer `upto` (2..5) and decode that layer's output (fp16 hi [+ lo] planes in its HBM layout) to fp32 [n][C][H][H].
+int ag_debug_tcx_layer(const ag_net_t* net, const float* d_patches, int n, int upto, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+    AG_REQUIRE(net && d_patches && d_out && d_ws, "NULL argument");
+    AG_REQUIRE(upto >= 2 && upto <= 5 && n >= 1, "layer out of range");
+    const size_t act = align_up(tcx_act_bytes(n), 256);
+    AG_REQUIRE(ws_bytes >= 2 * act, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)d_ws;
+    const tc::FirstSrc src = tc_src_patches(d_patches);
+    const bool hard = net->kind == AG_NET_HARDNET;
+    int rc = hard ? tcx_trunk_hardnet(net, src, n, n, nullptr, base, base + act, nullptr, st, upto)
+                  : tcx_trunk_affori(net, src, n, n, nullptr, base, base + act, nullptr, st, upto);
+    if (rc) return rc;
+    // layer l (2..5) writes: 2 -> bufB (L_S2_16, 32x32), 3 -> bufA (L_S1_16, 16x16), 4 -> bufB (L_S2_8P, 16x16), 5 -> bufA (L_S1_8P, 8x8)
+    const int lay = upto == 2 ? tcx::L_S2_16 : upto == 3 ? tcx::L_S1_16 : upto == 4 ? tcx::L_S2_8P : tcx::L_S1_8P;
+    const int H = upto == 2 ? 32 : (upto <= 4 ? 16 : 8);
+    const int Cb = hard ? 32 : 16;
+    const int C = upto == 2 ? Cb : (upto <= 4 ? 2 * Cb : 4 * Cb);
+    const void* buf = (upto == 2 || upto == 4) ? base + act : base;
+    tcx::tcx_decode_kernel<<<296, 256, 0, st>>>((const __half*)buf, lay, C, hard ? 0 : 1, H, n, d_out);
+    AG_CHECK_LAUNCH("tcx_decode_kernel");
+    return AG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,339 @@
+// Second-generation tensor-core (tcgen05) 3x3 convolution engine (sm_100a): row tiles without x padding, taps of one kernel row
+// stacked along N.
+//
+// Measured on B200 (tests/probe/tc_rates.cu): one tcgen05.mma kind::f16 (M = 128, K = 16) costs max(47.5, N/2) clk whatever its
+// operands' source, so an MMA with N = 16 .. 64 leaves 66 - 90 % of the tensor pipe idle.  The first-generation engine (tc_conv.cuh)
+// issued one MMA per tap (N = 16 .. 64); here the three taps of a kernel ROW share one MMA:
+//
+//   pixel planes are stored WITHOUT x padding, so that an M = 128 tile is 128 consecutive pixels = whole image rows (4 rows of 32,
+//   8 rows of 16, or 8 rows of 8 of TWO patches interleaved row by row), and every warp of the epilogue owns whole rows;
+//   for kernel row dy the A operand is the input plane advanced by dy rows (descriptor start address; a zero row above and below
+//   the plane in shared memory gives the y padding) and the B operand stacks the three taps of that row along N:
+//        D[q, (dx, c)] += sum_ci  in[q + (dy-1) W, ci] * w[dy][dx][ci][c]             one MMA per (dy, 16 input channels), N = 3 C
+//   the x shift moves to the epilogue:   out[p, c] = D[p-1, (0,c)] + D[p, (1,c)] + D[p+1, (2,c)]   (warp shuffles inside an image
+//   row; the neighbour outside the row is the zero padding).
+// Stride-2 layers read four parity planes; the taps dx = 0 and dx = 2 share the odd-x plane (N = 2 C), dx = 1 reads the even-x
+// plane (N = C):   out[x] = Dodd[x-1, dx0] + Dodd[x, dx2] + Deven[x, dx1].
+// Split precision as before: x = hi + lo fp16 planes (SA), w = hi + lo fp16 copies (SW), D = A_hi W_hi + A_hi W_lo + A_lo W_hi, each
+// product its own MMA into the SAME accumulator columns (at N >= 96 the MMAs are math bound, stacking hi | lo along N buys nothing).
+//
+// Activations between layers (HBM): fp16, 16-byte slots of 8 channels, [unit][channel group (hi groups, then lo groups)][plane][slot],
+// data rows only (the consumer's loader places them between zero rows in shared memory):
+//   L_S2_16  stride-2 consumer on a 32x32 map   unit = patch   4 parity planes x 256 slots  slot = (y/2)*16 + x/2, plane = (y&1)*2 + (x&1)
+//   L_S1_16  stride-1 consumer on a 16x16 map   unit = patch   256 slots                    slot = y*16 + x
+//   L_S2_8P  stride-2 consumer on a 16x16 map   unit = PAIR    4 parity planes x 128 slots  slot = ((y/2)*2 + p)*8 + x/2
+//   L_S1_8P  stride-1 consumer on an 8x8 map    unit = PAIR    128 slots                    slot = (y*2 + p)*8 + x       (p = patch & 1)
+//   L_HEAD   the 8x8 head GEMM's A operand (tc_head.cuh): [patch/128][pixel*C/8 + c/8][patch%128][8] (+ a residual plane behind it)
+//
+// Warp roles: 0 loader (cp.async.bulk per channel group and plane) | 1 MMA issuer | 2.. epilogue (4 warps per set, EW/4 sets taking
+// tiles in turn: one tcgen05.ld stream reads 43 B/clk per warp, so wide accumulators want more readers).
+#pragma once
+#include "tc_conv.cuh"
+
+namespace ag {
+namespace tcx {
+
+using namespace ag::tc;
+
+enum XLayout { L_S2_16 = 0, L_S1_16 = 1, L_S2_8P = 2, L_S1_8P = 3, L_HEAD = 4 };
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+
+// slots per channel group and unit of an HBM activation layout, and patches per unit
+__host__ __device__ constexpr int layout_slots(int lay) { return lay == L_S2_16 ? 1024 : lay == L_S1_16 ? 256 : lay == L_S2_8P ? 512 : 128; }
+__host__ __device__ constexpr int layout_pair(int lay) { return (lay == L_S2_8P || lay == L_S1_8P) ? 1 : 0; }
+// slot of pixel (y, x) of patch parity p in a layout
+__host__ __device__ constexpr int layout_slot(int lay, int y, int x, int p) {
+    return lay == L_S2_16 ? ((y & 1) * 2 + (x & 1)) * 256 + (y >> 1) * 16 + (x >> 1)
+         : lay == L_S1_16 ? y * 16 + x
+         : lay == L_S2_8P ? ((y & 1) * 2 + (x & 1)) * 128 + ((y >> 1) * 2 + p) * 8 + (x >> 1)
+                          : (y * 2 + p) * 8 + x;
+}
+
+// Geometry of a layer's input in shared memory.  H: input map edge, STRIDE 1 | 2.
+template <int H, int STRIDE>
+struct XIn {
+    static constexpr int HOUT = H / STRIDE;
+    static constexpr int PAIR = (HOUT == 8) ? 1 : 0;              // two patches per tile, interleaved row by row
+    static constexpr int W = HOUT;                                // pixels of one patch per image row
+    static constexpr int RW = W * (1 + PAIR);                     // slots per (interleaved) row
+    static constexpr int TILES = HOUT * RW / 128;                 // 8 | 2 | 1
+    static constexpr int NPLANES = (STRIDE == 1) ? 1 : 4;
+    static constexpr int DATA = HOUT * RW;                        // data slots per plane
+    static constexpr int PLANE = DATA + RW;                       // + one zero row above
+    static constexpr int SLOT_STAGE = NPLANES * PLANE;            // stride 1: the zero row BELOW a stage is the next stage's (or the group's trailing) zero row
+    static constexpr int LAYOUT = (STRIDE == 2) ? (PAIR ? L_S2_8P : L_S2_16) : (PAIR ? L_S1_8P : L_S1_16);
+    static_assert(HOUT == 8 || HOUT == 16 || HOUT == 32, "map sizes of the three nets");
+    static_assert(!(STRIDE == 1 && H == 32), "the 32x32 stride-1 layer lives in tcx_first.cuh");
+};
+
+struct XArgs {
+    const __half* in;     // HBM activation buffer in the layer's input layout
+    void* out;            // next layer's buffer
+    const __half* wpk;    // packed weights (tcx_pack_layer)
+    const float* bias;    // [COUT]
+    float inv_scale;      // 1 / (power-of-two scale of wpk)
+    int n, group;         // patches, patches per image
+    const int* count;     // valid patches per image (NULL: all)
+};
+
+// SA: input hi/lo planes; SW: weight hi/lo copies; OSA: write hi/lo planes.  OUT: layout of the output buffer.  EW: epilogue warps (4 | 8).
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW>
+struct XCfg {
+    using In = XIn<H, STRIDE>;
+    static constexpr int KC = CIN / 8, NT = COUT / NSPLIT, HOUT = In::HOUT;
+    static constexpr int G = KC * (1 + SA);                                   // channel groups of one unit
+    static constexpr int GS = STAGES * In::SLOT_STAGE + (STRIDE == 1 ? In::RW : 0);   // slots per channel group in shared memory
+    static constexpr int ACCW = 3 * NT;                                        // accumulator columns of one tile
+    static constexpr int NACC = (512 / ACCW) < 4 ? (512 / ACCW) : 4;
+    static constexpr uint32_t W_BYTES = 9u * CIN * NT * 2u * (1 + SW);         // per split
+    static constexpr uint32_t IN_BYTES = (uint32_t)G * GS * 16u;               // all stages
+    static constexpr uint32_t UNIT_IN_BYTES = (uint32_t)G * In::NPLANES * In::DATA * 16u;   // one unit in HBM
+    static constexpr int THREADS = 64 + 32 * EW;
+    static constexpr size_t SMEM = 1024 + (size_t)W_BYTES + IN_BYTES;
+    static constexpr int OUT_G = (COUT / 8) * (1 + OSA);
+    static constexpr size_t UNIT_OUT_BYTES = (OUT == L_HEAD) ? 0 : (size_t)OUT_G * layout_slots(OUT) * 16;
+    // weight rows per K group of one (dy, k step) block
+    static constexpr int NR1 = (1 + SW) * 3 * NT;                              // stride 1: [hi: dx0 dx1 dx2][lo: dx0 dx1 dx2]
+    static constexpr int NRO = (1 + SW) * 2 * NT, NRE = (1 + SW) * NT;         // stride 2: odd-x plane [hi: dx0 dx2][lo: ...], even-x plane [hi: dx1][lo: dx1]
+    static_assert(CIN % 16 == 0 && NT % 16 == 0 && ACCW <= 256 && NACC >= 2, "UMMA shape");
+    static_assert(EW == 4 || EW == 8, "epilogue warps");
+    static_assert(2 * STAGES + 2 * NACC + 1 <= 60, "barrier area");
+    static_assert(SMEM <= 232448, "shared memory budget");
+    static_assert(GS < 16384, "leading-byte offset field");
+    static_assert(OUT == L_HEAD || layout_pair(OUT) || !In::PAIR, "a pair layer writes pair layouts or the head operand");
+};
+
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a) {
+    using Cfg = XCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW>;
+    using In = typename Cfg::In;
+    constexpr int KC = Cfg::KC, NT = Cfg::NT, NACC = Cfg::NACC, TILES = In::TILES, HOUT = Cfg::HOUT, GS = Cfg::GS, RW = In::RW, W = In::W;
+    constexpr int PAIR = In::PAIR;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [STAGES]
+    uint64_t* empty = full + STAGES;                       // [STAGES]
+    uint64_t* tfull = empty + STAGES;                      // [NACC]
+    uint64_t* tempty = tfull + NACC;                       // [NACC]
+    uint64_t* wbar = tempty + NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    float* s_bias = reinterpret_cast<float*>(smem + 512);  // [NT]
+    unsigned char* sW = smem + 1024;
+    unsigned char* sIn = sW + Cfg::W_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.y;
+    const int n_units = PAIR ? (a.n + 1) >> 1 : a.n;
+
+    if (threadIdx.x < NT) s_bias[threadIdx.x] = a.bias[split * NT + threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < NACC; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // zero rows of every stage: written once, the loader only ever writes data rows
+    for (int i = threadIdx.x; i < (int)(Cfg::IN_BYTES / 16); i += blockDim.x) reinterpret_cast<uint4*>(sIn)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    auto pvalid = [&](int pi) -> bool { return pi < a.n && (a.count == nullptr || (pi % a.group) < a.count[pi / a.group]); };
+    auto uvalid = [&](int u) -> bool { return PAIR ? (pvalid(2 * u) || pvalid(2 * u + 1)) : pvalid(u); };
+
+    if (warp == 0) {
+        // ===== loader =====
+        if (lane == 0) {
+            mbar_expect_tx(wbar, Cfg::W_BYTES);
+            bulk_g2s(sW, reinterpret_cast<const unsigned char*>(a.wpk) + (size_t)split * Cfg::W_BYTES, Cfg::W_BYTES, wbar);
+            int it = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                if (!uvalid(u)) continue;
+                const int s = it % STAGES;
+                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], Cfg::UNIT_IN_BYTES);
+                const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.in) + (size_t)u * Cfg::UNIT_IN_BYTES;
+#pragma unroll 1
+                for (int g = 0; g < Cfg::G; g++)
+#pragma unroll
+                    for (int pl = 0; pl < In::NPLANES; pl++)
+                        bulk_g2s(sIn + ((size_t)g * GS + (size_t)s * In::SLOT_STAGE + (size_t)pl * In::PLANE + RW) * 16,
+                                 gsrc + ((size_t)g * In::NPLANES + pl) * In::DATA * 16, In::DATA * 16u, &full[s]);
+                it++;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (warp-uniform control flow, one elected lane issues) =====
+        constexpr uint32_t idesc3 = (1u << 4) | ((uint32_t)((3 * NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t leader = elect_one();
+        mbar_wait(wbar, 0);
+        tc_fence_after();
+        const uint32_t w_base = smem_u32(sW) >> 4;           // 16-byte units
+        const uint32_t in_base = smem_u32(sIn) >> 4;
+        constexpr uint32_t LBO_A = ((uint32_t)GS) << 16;      // (bytes >> 4) << 16
+        int it = 0, tcnt = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            if (!uvalid(u)) continue;
+            const int s = it % STAGES;
+            mbar_wait(&full[s], (it / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t st_base = in_base + (uint32_t)(s * In::SLOT_STAGE);
+#pragma unroll 1
+            for (int t = 0; t < TILES; t++, tcnt++) {
+                const int ab = tcnt % NACC;
+                mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t d = tmem + (uint32_t)(ab * Cfg::ACCW);
+                    const uint32_t a_t = st_base + (uint32_t)(t * 128);
+                    if (STRIDE == 1) {
+#pragma unroll
+                        for (int dy = 0; dy < 3; dy++) {
+#pragma unroll
+                            for (int j = 0; j < KC / 2; j++) {
+                                const uint32_t ahi = ((a_t + (uint32_t)(dy * RW + 2 * j * GS)) & 0x3FFFu) | LBO_A;
+                                const uint32_t alo = ((a_t + (uint32_t)(dy * RW + (KC + 2 * j) * GS)) & 0x3FFFu) | LBO_A;
+                                const uint32_t blk = w_base + (uint32_t)((dy * (KC / 2) + j) * 2 * Cfg::NR1);
+                                const uint32_t bhi = (blk & 0x3FFFu) | ((uint32_t)Cfg::NR1 << 16), blo = ((blk + 3 * NT) & 0x3FFFu) | ((uint32_t)Cfg::NR1 << 16);
+                                if (dy == 0 && j == 0) umma_f16_lo<0>(d, ahi, bhi, idesc3); else umma_f16_lo<1>(d, ahi, bhi, idesc3);
+                                if (SW) umma_f16_lo<1>(d, ahi, blo, idesc3);
+                                if (SA) umma_f16_lo<1>(d, alo, bhi, idesc3);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int dy = 0; dy < 3; dy++) {
+                            constexpr int PL = In::PLANE;
+                            const int py = (dy == 1) ? 0 : 1, ro = (dy == 0) ? 0 : 1;
+#pragma unroll
+                            for (int j = 0; j < KC / 2; j++) {
+                                const uint32_t blk = w_base + (uint32_t)((dy * (KC / 2) + j) * 2 * (Cfg::NRO + Cfg::NRE));
+                                const uint32_t bo_hi = (blk & 0x3FFFu) | ((uint32_t)Cfg::NRO << 16), bo_lo = ((blk + 2 * NT) & 0x3FFFu) | ((uint32_t)Cfg::NRO << 16);
+                                const uint32_t be = blk + 2 * Cfg::NRO;
+                                const uint32_t be_hi = (be & 0x3FFFu) | ((uint32_t)Cfg::NRE << 16), be_lo = ((be + NT) & 0x3FFFu) | ((uint32_t)Cfg::NRE << 16);
+                                // odd-x plane (px = 1): taps dx = 0 and dx = 2
+                                const uint32_t ao = a_t + (uint32_t)((py * 2 + 1) * PL + ro * RW);
+                                const uint32_t ao_hi = ((ao + (uint32_t)(2 * j * GS)) & 0x3FFFu) | LBO_A, ao_lo = ((ao + (uint32_t)((KC + 2 * j) * GS)) & 0x3FFFu) | LBO_A;
+                                if (dy == 0 && j == 0) umma_f16_lo<0>(d, ao_hi, bo_hi, idesc2); else umma_f16_lo<1>(d, ao_hi, bo_hi, idesc2);
+                                if (SW) umma_f16_lo<1>(d, ao_hi, bo_lo, idesc2);
+                                if (SA) umma_f16_lo<1>(d, ao_lo, bo_hi, idesc2);
+                                // even-x plane (px = 0): tap dx = 1
+                                const uint32_t ae = a_t + (uint32_t)((py * 2 + 0) * PL + ro * RW);
+                                const uint32_t ae_hi = ((ae + (uint32_t)(2 * j * GS)) & 0x3FFFu) | LBO_A, ae_lo = ((ae + (uint32_t)((KC + 2 * j) * GS)) & 0x3FFFu) | LBO_A;
+                                const uint32_t de = d + (uint32_t)(2 * NT);
+                                if (dy == 0 && j == 0) umma_f16_lo<0>(de, ae_hi, be_hi, idesc1); else umma_f16_lo<1>(de, ae_hi, be_hi, idesc1);
+                                if (SW) umma_f16_lo<1>(de, ae_hi, be_lo, idesc1);
+                                if (SA) umma_f16_lo<1>(de, ae_lo, be_hi, idesc1);
+                            }
+                        }
+                    }
+                    umma_commit(&tfull[ab]);
+                }
+                __syncwarp();
+            }
+            if (leader) umma_commit(&empty[s]);
+            __syncwarp();
+            it++;
+        }
+    } else {
+        // ===== epilogue: EW / 4 sets of four warps (TMEM lane quadrant = warp % 4), set k takes tiles k, k + NSETS, ... =====
+        constexpr int NSETS = EW / 4;
+        const int q = warp & 3;
+        const int set = (warp - 2) >> 2;
+        const int r = q * 32 + lane;                         // tile row of this thread
+        int tcnt = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            if (!uvalid(u)) continue;
+#pragma unroll 1
+            for (int t = 0; t < TILES; t++, tcnt++) {
+                if ((tcnt % NSETS) != set) continue;
+                const int ab = tcnt % NACC;
+                mbar_wait(&tfull[ab], (tcnt / NACC) & 1);
+                tc_fence_after();
+                // pixel of this row
+                int y, x, p, pi;
+                if (PAIR) { y = r >> 4; p = (r >> 3) & 1; x = r & 7; pi = 2 * u + p; }
+                else { const int m = t * 128 + r; y = m / W; x = m - y * W; p = u & 1; pi = u; }
+                const bool ok = pvalid(pi);
+                const bool has_l = x > 0, has_r = x < W - 1;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACCW);
+                // output position
+                unsigned char* obase = nullptr;
+                size_t lo_off = 0;
+                if (OUT == L_HEAD) {
+                    obase = reinterpret_cast<unsigned char*>(a.out) + (((size_t)(pi >> 7) * (HOUT * HOUT * COUT / 8) + (size_t)(y * HOUT + x) * (COUT / 8)) * 128 + (pi & 127)) * 16;
+                    lo_off = (size_t)((a.n + 127) >> 7) * (HOUT * HOUT * COUT / 8) * 128 * 16;
+                } else {
+                    const int ou = layout_pair(OUT) ? (pi >> 1) : pi;
+                    obase = reinterpret_cast<unsigned char*>(a.out) + (size_t)ou * Cfg::UNIT_OUT_BYTES + (size_t)layout_slot(OUT, y, x, pi & 1) * 16;
+                    lo_off = (size_t)(COUT / 8) * layout_slots(OUT) * 16;
+                }
+#pragma unroll 1
+                for (int c0 = 0; c0 < NT; c0 += 16) {
+                    uint32_t r0[16], r1[16], r2[16];
+                    tmem_ld16(taddr + (uint32_t)c0, r0);                   // stride 1: dx0 | stride 2: odd plane dx0
+                    tmem_ld16(taddr + (uint32_t)(NT + c0), r1);            // stride 1: dx1 | stride 2: odd plane dx2
+                    tmem_ld16(taddr + (uint32_t)(2 * NT + c0), r2);        // stride 1: dx2 | stride 2: even plane dx1
+                    tmem_ld_wait();
+                    if (c0 + 16 >= NT) {   // last column chunk read: release the accumulator buffer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[ab]);
+                    }
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[i]), 1, W);
+                        float acc;
+                        if (STRIDE == 1) {
+                            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[i]), 1, W);
+                            acc = __uint_as_float(r1[i]) + ((has_l ? left : 0.f) + (has_r ? right : 0.f));
+                        } else {
+                            acc = (__uint_as_float(r1[i]) + __uint_as_float(r2[i])) + (has_l ? left : 0.f);
+                        }
+                        v[i] = fmaxf(fmaf(acc, a.inv_scale, s_bias[c0 + i]), 0.f);
+                    }
+                    if (ok) {
+#pragma unroll
+                        for (int g = 0; g < 2; g++) {
+                            const int cg = (split * NT + c0) / 8 + g;       // channel group of the output
+                            const size_t goff = (OUT == L_HEAD) ? (size_t)cg * 128 * 16 : (size_t)cg * layout_slots(OUT) * 16;
+                            uint4 pk;
+                            pk.x = pack_h2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_h2(v[g * 8 + 2], v[g * 8 + 3]);
+                            pk.z = pack_h2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_h2(v[g * 8 + 6], v[g * 8 + 7]);
+                            *reinterpret_cast<uint4*>(obase + goff) = pk;
+                            if (OSA) {
+                                float l[8];
+#pragma unroll
+                                for (int e = 0; e < 8; e++) l[e] = v[g * 8 + e] - __half2float(__float2half_rn(v[g * 8 + e]));
+                                pk.x = pack_h2(l[0], l[1]); pk.y = pack_h2(l[2], l[3]); pk.z = pack_h2(l[4], l[5]); pk.w = pack_h2(l[6], l[7]);
+                                *reinterpret_cast<uint4*>(obase + lo_off + goff) = pk;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
+}  // namespace tcx
+}  // namespace ag

@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """Benchmark of the HesAffNet + HardNet detect-and-describe hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|5] [--batch B] [--impl ours|reference]
 
 One "step" = one pass of the whole path (pyramid -> Hessian/NMS -> top-k -> sample -> AffNet -> filter -> sample
--> OriNet -> sample -> HardNet) over one batch of B synthetic 1024x768 images, K=2000 keypoints each, per GPU
-(BASELINE.json configs[1] tiled B times = configs[3]'s per-GPU shard).  N>1: one process per GPU (torchrun), B
-images per rank (weak scaling), one NCCL all-gather of descriptors/LAFs/counts per step.  Prints ONE JSON line.
+-> OriNet -> sample -> HardNet) over one batch of B synthetic images per GPU.  Headline workload (--config 2, the default):
+1024x768, K=2000 keypoints, B=16 (BASELINE.json configs[1] tiled B times = configs[3]'s per-GPU shard).  --config 3: 1920x1080, K=4000,
+B=64; --config 5: 3840x2160, K=8000, border=33 (the 5-octave pyramid), B=1.  N>1: one process per GPU (torchrun), B images per rank
+(weak scaling), one NCCL all-gather of descriptors/LAFs/counts per step.  Prints ONE JSON line; with the default config the line
+also carries `extra`: the same metric for B=1, B=64 (configs[3] as written) and configs 3 and 5.
 """
 import argparse
 import json
@@ -17,18 +19,30 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-H, W, K = 768, 1024, 2000
+CONFIGS = {   # BASELINE.json configs[...]: (H, W, K, border, default batch per GPU, label)
+    "2": (768, 1024, 2000, 5, 16, "configs[1] tiled = configs[3] shard"),
+    "3": (1080, 1920, 4000, 5, 64, "configs[2]"),
+    "5": (2160, 3840, 8000, 33, 1, "configs[4] (border=33: the 5-octave pyramid)"),
+}
 ALG_BYTES_PER_PX = 30.66                      # detect stage, 4 B read + 5 levels x 4 B x 1.333 written
 FLOP_PER_PATCH = {"affnet": 19.19e6, "orinet": 19.32e6, "hardnet": 78.18e6}   # 2*MAC, SURVEY.md §8(d)
-# 2*MAC of each conv layer kernel, per patch (for the per-kernel roofline)
-HARD_LAYER_FLOP = [2 * 294912, 2 * 9437184, 2 * 4718592, 2 * 9437184, 2 * 4718592, 2 * 9437184, 2 * 1048576]
+DTYPE = "fp16 operands (fp16 residual planes: AffNet/OriNet weights+activations, HardNet layer 2-4 weights), fp32 accumulate; stencils fp32"
+
+
+def oracle_module():
+    """The CPU oracle: imported ONLY by the CPU legs (cpu_baseline / --impl reference), never by the product arm."""
+    op = os.path.join(ROOT, "oracle")
+    if op not in sys.path:
+        sys.path.insert(0, op)
+    import affnet_oracle
+    return affnet_oracle
 
 
 def ncu_traffic(batch):
@@ -52,9 +66,9 @@ def peaks():
     return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, src="fallback")
 
 
-def make_images(B, seed0):
-    import affnet_oracle as O
-    return torch.cat([O.synthetic_image(H, W, seed0 + i) for i in range(B)])
+def make_images(B, seed0, H, W):
+    from helpers import synthetic_image
+    return torch.cat([synthetic_image(H, W, seed0 + i) for i in range(B)])
 
 
 def load_state_dicts():
@@ -109,10 +123,10 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def best_cpu_threads():
+def best_cpu_threads(H, W):
     """Pick the torch thread count that runs the reference's dominant CPU cost (HardNet on a patch batch + one
     dense blur) fastest on this host: all cores is NOT the fastest on a 128-core box (measured 40x slower)."""
-    import affnet_oracle as O
+    O = oracle_module()
     sd = load_state_dicts()
     P = torch.rand(256, 1, 32, 32)
     x = torch.rand(1, 1, H, W)
@@ -129,42 +143,63 @@ def best_cpu_threads():
     return best
 
 
-def cpu_reference_leg(n_images, threads):
-    """The reference's algorithm on host cores: oracle port (oracle/affnet_oracle.py)."""
-    import affnet_oracle as O
-    torch.set_num_threads(threads)
-    sd = load_state_dicts()
-    imgs = make_images(n_images, 1234)
-    O.detect_and_describe(imgs[0:1], sd["affnet"], sd["orinet"], sd["hardnet"], K, do_ori=True)  # warm-up
-    t0 = time.perf_counter()
-    n_desc = 0
-    for i in range(n_images):
-        dL, r, d = O.detect_and_describe(imgs[i:i + 1], sd["affnet"], sd["orinet"], sd["hardnet"], K, do_ori=True)
-        n_desc += d.shape[0]
-    dt = time.perf_counter() - t0
-    return dt, n_images * H * W / dt / 1e6, n_desc / dt / 1e3
+class CpuArm:
+    """The reference's own CPU implementation of the path: the UNMODIFIED reference through oracle/ref_harness.py when its tree is
+    present ($AFFNET_REF, /root/reference, baseline/_ref; kind "reference"), else the oracle port (kind "port").  The reference is
+    Python with neither setup.py nor pyproject.toml: it cannot be pip-installed into baseline/_ref and does not travel to the GPU box."""
+
+    def __init__(self, H, W, K, border):
+        O = oracle_module()
+        self.O, self.H, self.W, self.K, self.border = O, H, W, K, border
+        self.sd = load_state_dicts()
+        self.kind, self.what = "port", "oracle/affnet_oracle.py (PyTorch-CPU restatement; the reference tree is absent on this host)"
+        try:
+            import ref_harness as R
+            if R.available():
+                aff, ori, hn = R.load_nets()
+                self.det = R.make_detector(aff, ori, num_features=K, border=border)
+                self.hn, self.R = hn, R
+                self.kind, self.what = "reference", "the unmodified reference at %s through oracle/ref_harness.py::run_full (train_AffNet_test_on_graffity.py:255-260)" % R.REF
+        except Exception as e:   # noqa: BLE001
+            self.what += " [reference import failed: %s]" % e
+
+    def one(self, img):
+        if self.kind == "reference":
+            LAFs, resp, patches, d = self.R.run_full(self.det, self.hn, img, True)
+            return d.shape[0]
+        dL, r, d = self.O.detect_and_describe(img, self.sd["affnet"], self.sd["orinet"], self.sd["hardnet"], self.K, border=self.border, do_ori=True)
+        return d.shape[0]
+
+    def leg(self, imgs, threads):
+        torch.set_num_threads(threads)
+        self.one(imgs[0:1])   # warm-up
+        t0 = time.perf_counter()
+        n_desc = sum(self.one(imgs[i:i + 1]) for i in range(imgs.size(0)))
+        dt = time.perf_counter() - t0
+        return dt, imgs.size(0) * self.H * self.W / dt / 1e6, n_desc / dt / 1e3
 
 
 def run_reference(args, rank, world, real_stdout):
     if rank != 0:
         return
-    threads = best_cpu_threads()
-    per = max(1, args.ref_images)
-    for _ in range(args.warmup):
-        pass  # cpu_reference_leg warms up once per call
+    H, W, K, border, _, label = CONFIGS[args.config]
+    threads = best_cpu_threads(H, W)
+    per = max(1, min(args.ref_images, 24 // max(1, args.steps)))     # bounded sample: at most ~24 images in the whole run
+    arm = CpuArm(H, W, K, border)
+    imgs = make_images(per, 1234, H, W)
     times, mpix, kp = [], [], []
     for _ in range(max(1, args.steps)):
-        dt, m, k = cpu_reference_leg(per, threads)
+        dt, m, k = arm.leg(imgs, threads)
         times.append(dt); mpix.append(m); kp.append(k)
     v = float(np.mean(mpix))
     line = {"impl": "reference", "metric": "Mpix/s end-to-end HesAffNet(+OriNet)+HardNet", "value": v, "unit": "Mpix/s",
             "kpatches_per_s": float(np.mean(kp)), "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic images (seeded noise, blur sigma 2, stretched), pretrained weights from tests/golden",
-            "config": {"workload": "%dx%d grayscale, %d kpts/img, %d image(s) per step (bounded CPU sample of the batch)" % (W, H, K, per),
-                       "do_ori": True, "border": 5, "mrSize": 5.192},
-            "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
-                             "sample": "%d image(s) of the workload per step, oracle/affnet_oracle.py (PyTorch-CPU restatement; the reference itself is Python and cannot travel)" % per},
+            "config": {"workload": "%dx%d grayscale, %d kpts/img, %d image(s) per step (bounded CPU sample of the batch; %s)" % (W, H, K, per, label),
+                       "do_ori": True, "border": border, "mrSize": 5.192},
+            "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": threads, "host_cores": os.cpu_count(), "kind": arm.kind,
+                             "sample": "%d image(s) of the workload per step, %s" % (per, arm.what)},
             "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(real_stdout, line)
 
@@ -183,16 +218,190 @@ def emit(real_stdout, line):
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
+TC_FAMILY = ("tc_first2_kernel", "tc_conv_kernel", "tc_conv_pair_kernel", "tc_head_kernel", "tc_headx_kernel", "tcx_first_kernel", "tcx_conv_kernel")
+STENCIL = ("blur_kernel", "octave_kernel", "pyramid_tail_kernel", "detect_level_kernel", "detect_fused_kernel", "detect_warp_kernel", "resolve_kernel")
+
+
+class Workload:
+    """One configuration on this rank's GPU: pipeline, inputs, device-resident and end-to-end timed legs."""
+
+    def __init__(self, ctx, H, W, K, border, B, use_graph):
+        from affnet_b200.pipeline import DetectDescribePipeline
+        self.ctx, self.H, self.W, self.K, self.border, self.B, self.use_graph = ctx, H, W, K, border, B, use_graph
+        dev, rank, world = ctx["dev"], ctx["rank"], ctx["world"]
+        a, o, h = ctx["nets"]
+        self.pipe = DetectDescribePipeline(B, H, W, a, h, o, num_features=K, border=border, do_ori=True, device=dev)
+        self.host_imgs = make_images(B, 1234 + rank * B, H, W).pin_memory()
+        self.dev_imgs = self.host_imgs.to(dev)
+        self.xchg = None
+        if world > 1:
+            from affnet_b200.exchange import DescriptorExchange
+            self.xchg = DescriptorExchange(world, B, K, dev)   # one all-gather per step, overlapped with the next step
+        self.last = [None, None, None, None]
+        if use_graph:
+            self.pipe.capture()
+
+    def step_device(self):
+        out = self.pipe.replay(self.dev_imgs) if self.use_graph else self.pipe.run(self.dev_imgs)
+        if self.xchg:
+            self.xchg.submit(out[0], out[2], out[3])
+        self.last[:] = out
+        return out
+
+    def timed(self, steps, warmup, sampler=None):
+        ctx = self.ctx
+        dist, dev, flush = ctx["dist"], ctx["dev"], ctx["flush"]
+        for _ in range(warmup):
+            self.step_device()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_begin = time.time()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1.0)                                  # L2 flush between timed iterations (outside the events)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); self.step_device(); e1.record()
+            evs.append((e0, e1))
+        if self.xchg:   # the last steps' all-gathers finish inside the timed region
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); self.xchg.drain(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        t_stop = time.time()
+        clocks = None
+        if sampler:
+            # The sampler runs since before the warm-up; only samples that arrived inside the timed region count.  If the region was
+            # too short for three of them, the same load keeps running (untimed, rank 0 only, hence without collectives) until it is.
+            extra, t_end = 0, time.time() + 4.0
+            while sampler.in_window(t_begin, time.time()) < 3 and time.time() < t_end:
+                (self.pipe.replay(self.dev_imgs) if self.use_graph else self.pipe.run(self.dev_imgs)); torch.cuda.synchronize(); extra += 1
+            clocks = sampler.stop(window=(t_begin, time.time() if extra else t_stop))
+            clocks["sampled"] = "inside the timed region" if extra == 0 else "timed region + %d extra untimed steps of the same load" % extra
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = sum(a_.elapsed_time(b_) for a_, b_ in evs)
+        t = torch.tensor([total_ms], device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), clocks
+
+    def check_exchange(self):
+        if not self.xchg:
+            return
+        rank, B = self.ctx["rank"], self.B
+        self.xchg.drain(); torch.cuda.synchronize()
+        gd, gl, gc = self.xchg.last()
+        own = slice(rank * B, (rank + 1) * B)
+        if not (torch.equal(gc[own], self.pipe.count.int()) and bool((gc > 0).all()) and torch.equal(gd[own], self.last[2]) and torch.equal(gl[own], self.last[0])):
+            raise RuntimeError("all-gather returned something else than this rank's results")
+
+    def timed_e2e(self, steps, warmup):
+        """Every step uploads ITS OWN batch from pinned host memory and downloads ITS OWN results.  Transfers run on copy streams and are
+        software-pipelined against the compute of the neighbouring steps (double-buffered device staging), as a serving loop would do;
+        all of it is inside the timed region: ONE event pair around all steps, closed after the last results reached host memory."""
+        ctx = self.ctx
+        dist, dev = ctx["dist"], ctx["dev"]
+        B, K, pipe, use_graph, xchg = self.B, self.K, self.pipe, self.use_graph, self.xchg
+        host_desc = torch.empty(B, K, 128).pin_memory(); host_lafs = torch.empty(B, K, 2, 3).pin_memory()
+        host_resp = torch.empty(B, K).pin_memory(); host_cnt = torch.empty(B, dtype=torch.int32).pin_memory()
+        copy_stream = torch.cuda.Stream(device=dev)     # device -> host
+        up_stream = torch.cuda.Stream(device=dev)       # host -> device (separate, so uploads never queue behind a download)
+        stage_in = [torch.empty_like(self.dev_imgs) for _ in range(2)]
+        stage_out = [(torch.empty(B, K, 128, device=dev), torch.empty(B, K, 2, 3, device=dev), torch.empty(B, K, device=dev),
+                      torch.empty(B, dtype=torch.int32, device=dev)) for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        state = {"i": 0}
+
+        def upload(slot):
+            with torch.cuda.stream(up_stream):
+                stage_in[slot].copy_(self.host_imgs, non_blocking=True)
+                ev_in[slot].record(up_stream)
+
+        def step():
+            i = state["i"]; slot = i & 1
+            cur = torch.cuda.current_stream()
+            if i == 0:
+                upload(slot)
+            cur.wait_event(ev_in[slot])                       # this step's images are on the device
+            ev_free = torch.cuda.Event(); ev_free.record(cur)
+            up_stream.wait_event(ev_free)                     # the other input slot was consumed by the previous step
+            upload(slot ^ 1)                                  # next step's images travel while this step computes
+            out = pipe.replay(stage_in[slot]) if use_graph else pipe.run(stage_in[slot])
+            if xchg:
+                xchg.submit(out[0], out[2], out[3])
+            if i >= 2:
+                cur.wait_event(ev_done[slot])                 # the download that used this staging slot two steps ago has finished
+            so = stage_out[slot]
+            so[0].copy_(out[2], non_blocking=True); so[1].copy_(out[0], non_blocking=True); so[2].copy_(out[1], non_blocking=True); so[3].copy_(out[3], non_blocking=True)
+            ev_out[slot].record(cur)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_out[slot])
+                host_desc.copy_(so[0], non_blocking=True); host_lafs.copy_(so[1], non_blocking=True)
+                host_resp.copy_(so[2], non_blocking=True); host_cnt.copy_(so[3], non_blocking=True)
+                ev_done[slot].record(copy_stream)
+            state["i"] = i + 1
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        if xchg:
+            xchg.drain()
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        torch.cuda.current_stream().wait_stream(up_stream)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def summary(self, steps, warmup, e2e=True):
+        """Device-resident + end-to-end throughput of this configuration (for the `extra` block)."""
+        total_ms, _ = self.timed(steps, warmup)
+        self.pipe.check()
+        self.check_exchange()
+        world = self.ctx["world"]
+        pix = world * self.B * self.H * self.W
+        n_desc = int(self.pipe.count.sum().item())
+        ms = total_ms / steps
+        out = {"workload": "%dx%d, %d kpts/img, border %d, %d image(s) per GPU per step" % (self.W, self.H, self.K, self.border, self.B),
+               "value": pix / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": ms, "kpatches_per_s": world * n_desc / (ms * 1e-3) / 1e3, "steps": steps}
+        if e2e:
+            e_ms = self.timed_e2e(steps, warmup) / steps
+            out["e2e"] = {"value": pix / (e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": e_ms,
+                          "h2d_bytes_per_step": self.B * self.H * self.W * 4, "d2h_bytes_per_step": self.B * self.K * (128 + 6 + 1) * 4 + self.B * 4}
+        return out
+
+    def close(self):
+        self.pipe = None
+        self.xchg = None
+        torch.cuda.empty_cache()
+
+
 def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--config", default="2", choices=sorted(CONFIGS), help="BASELINE.json configuration (2 = headline)")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the configuration's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-images", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra configurations (B=1, B=64, configs 3 and 5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -214,149 +423,26 @@ def _main(real_stdout):
     import affnet_b200._lib as L
     from affnet_b200.architectures import AffNetFast, OriNetFast
     from affnet_b200.HardNet import HardNet
-    from affnet_b200.pipeline import DetectDescribePipeline
     sd = load_state_dicts()
     a, o, h = AffNetFast(PS=32), OriNetFast(PS=32), HardNet()
     a.load_state_dict(sd["affnet"]); o.load_state_dict(sd["orinet"]); h.load_state_dict(sd["hardnet"])
     a, o, h = a.eval().to(dev), o.eval().to(dev), h.eval().to(dev)
-    B = args.batch
+    H, W, K, border, B0, label = CONFIGS[args.config]
+    B = args.batch or B0
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()   # nvidia-smi needs a few hundred ms to deliver its first sample: start it long before the timed region
-    pipe = DetectDescribePipeline(B, H, W, a, h, o, num_features=K, do_ori=True, device=dev)
-    host_imgs = make_images(B, 1234 + rank * B).pin_memory()
-    dev_imgs = host_imgs.to(dev)
-    host_desc = torch.empty(B, K, 128).pin_memory(); host_lafs = torch.empty(B, K, 2, 3).pin_memory()
-    host_resp = torch.empty(B, K).pin_memory(); host_cnt = torch.empty(B, dtype=torch.int32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
-    from affnet_b200.exchange import DescriptorExchange
-    xchg = DescriptorExchange(world, B, K, dev) if world > 1 else None   # one all-gather per step, overlapped with the next step
-    step_out_ref = [None, None, None, None]
-
+    ctx = {"dev": dev, "dist": dist, "rank": rank, "world": world, "nets": (a, o, h), "flush": flush}
     use_graph = not args.no_graph
-    if use_graph:
-        pipe.capture()
+    wl = Workload(ctx, H, W, K, border, B, use_graph)
+    pipe = wl.pipe
 
-    def step_device():
-        if use_graph:
-            out = pipe.replay(dev_imgs)
-        else:
-            out = pipe.run(dev_imgs)
-        if xchg:
-            xchg.submit(out[0], out[2], out[3])
-        step_out_ref[:] = out
-        return out
-
-    # End-to-end leg: every step uploads ITS OWN batch from pinned host memory and downloads ITS OWN results.  Transfers run on
-    # a copy stream and are software-pipelined against the compute of the neighbouring steps (double-buffered device staging),
-    # as a serving loop would do; all of it is inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)     # device -> host
-    up_stream = torch.cuda.Stream(device=dev)       # host -> device (separate, so uploads never queue behind a download)
-    stage_in = [torch.empty_like(dev_imgs) for _ in range(2)]
-    stage_out = [(torch.empty(B, K, 128, device=dev), torch.empty(B, K, 2, 3, device=dev), torch.empty(B, K, device=dev),
-                  torch.empty(B, dtype=torch.int32, device=dev)) for _ in range(2)]
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
-    e2e_state = {"i": 0}
-
-    def upload(slot):
-        with torch.cuda.stream(up_stream):
-            stage_in[slot].copy_(host_imgs, non_blocking=True)
-            ev_in[slot].record(up_stream)
-
-    def step_e2e():
-        i = e2e_state["i"]; slot = i & 1
-        cur = torch.cuda.current_stream()
-        if i == 0:
-            upload(slot)
-        cur.wait_event(ev_in[slot])                       # this step's images are on the device
-        ev_free = torch.cuda.Event(); ev_free.record(cur)
-        up_stream.wait_event(ev_free)                     # the other input slot was consumed by the previous step
-        upload(slot ^ 1)                                  # next step's images travel while this step computes
-        out = pipe.replay(stage_in[slot]) if use_graph else pipe.run(stage_in[slot])
-        if xchg:
-            xchg.submit(out[0], out[2], out[3])
-        if i >= 2:
-            cur.wait_event(ev_done[slot])                 # the download that used this staging slot two steps ago has finished
-        so = stage_out[slot]
-        so[0].copy_(out[2], non_blocking=True); so[1].copy_(out[0], non_blocking=True); so[2].copy_(out[1], non_blocking=True); so[3].copy_(out[3], non_blocking=True)
-        ev_out[slot].record(cur)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_out[slot])
-            host_desc.copy_(so[0], non_blocking=True); host_lafs.copy_(so[1], non_blocking=True)
-            host_resp.copy_(so[2], non_blocking=True); host_cnt.copy_(so[3], non_blocking=True)
-            ev_done[slot].record(copy_stream)
-        e2e_state["i"] = i + 1
-
-    def timed(fn, steps, warmup, sampler=None):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t_begin = time.time()
-        evs = []
-        for _ in range(steps):
-            flush.fill_(1.0)                                  # L2 flush between timed iterations (outside the events)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); fn(); e1.record()
-            evs.append((e0, e1))
-        if xchg:   # the last steps' all-gathers finish inside the timed region
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); xchg.drain(); e1.record()
-            evs.append((e0, e1))
-        torch.cuda.synchronize()
-        t_stop = time.time()
-        clocks = None
-        if sampler:
-            # The sampler runs since before the warm-up; only samples that arrived inside the timed region count.  If the region was
-            # too short for three of them, the same load keeps running (untimed, rank 0 only, hence without collectives) until it is.
-            extra, t_end = 0, time.time() + 4.0
-            while sampler.in_window(t_begin, time.time()) < 3 and time.time() < t_end:
-                (pipe.replay(dev_imgs) if use_graph else pipe.run(dev_imgs)); torch.cuda.synchronize(); extra += 1
-            clocks = sampler.stop(window=(t_begin, time.time() if extra else t_stop))
-            clocks["sampled"] = "inside the timed region" if extra == 0 else "timed region + %d extra untimed steps of the same load" % extra
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        total_ms = sum(a_.elapsed_time(b_) for a_, b_ in evs)
-        t = torch.tensor([total_ms], device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), clocks
-
-    total_ms, clocks = timed(step_device, args.steps, args.warmup, sampler)
+    total_ms, clocks = wl.timed(args.steps, args.warmup, sampler)
     pipe.check()
-    if xchg:   # the exchange delivered this rank's own block intact and every rank's counts
-        xchg.drain(); torch.cuda.synchronize()
-        gd, gl, gc = xchg.last()
-        own = slice(rank * B, (rank + 1) * B)
-        if not (torch.equal(gc[own], pipe.count.int()) and bool((gc > 0).all()) and torch.equal(gd[own], step_out_ref[2]) and torch.equal(gl[own], step_out_ref[0])):
-            raise RuntimeError("all-gather returned something else than this rank's results")
+    wl.check_exchange()
     n_desc = int(pipe.count.sum().item())
-    # e2e timing: ONE event pair around all K steps, closed only after the last step's results have reached host memory
-    for _ in range(args.warmup):
-        step_e2e()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    if xchg:
-        xchg.drain()
-    torch.cuda.current_stream().wait_stream(copy_stream)
-    torch.cuda.current_stream().wait_stream(up_stream)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms = wl.timed_e2e(args.steps, args.warmup)
 
     # ---- per-kernel CUDA-event profile of the same step (non-graph launch path), rank 0 ---------------------------
     roof = None
@@ -365,7 +451,7 @@ def _main(real_stdout):
         prof_steps = 3
         for i in range(prof_steps):
             flush.fill_(1.0)
-            lst = L.profile(lambda: pipe.run(dev_imgs))
+            lst = L.profile(lambda: pipe.run(wl.dev_imgs))
             if i == prof_steps - 1:
                 order = [(k, round(ms, 4)) for k, ms in lst]
             for name, ms in lst:
@@ -373,45 +459,55 @@ def _main(real_stdout):
         step_ms = sum(sum(v) for v in per_kernel.values()) / prof_steps
         agg = sorted(((sum(v) / prof_steps, len(v) // prof_steps, k) for k, v in per_kernel.items()), reverse=True)
         pk = peaks()
-        # dominant kernel family: every tcgen05 kernel of the three CNNs (layers 1+2 fused in tc_first2_kernel, layers 3-6 in
-        # tc_conv_kernel / tc_conv_pair_kernel, the 8x8 head GEMMs in tc_head_kernel / tc_headx_kernel)
+        # dominant kernel family: every tcgen05 kernel of the three CNNs (layers 1+2 fused with the sampler in the "first" kernels, layers 3-6 in
+        # the conv kernels, the 8x8 head GEMMs in tc_head_kernel / tc_headx_kernel)
         n_aff, n_ori, n_hard = B * int(1.5 * K), n_desc, n_desc
-        TC_FAMILY = ("tc_first2_kernel", "tc_conv_kernel", "tc_conv_pair_kernel", "tc_head_kernel", "tc_headx_kernel")
         tc_flop = n_aff * FLOP_PER_PATCH["affnet"] + n_ori * FLOP_PER_PATCH["orinet"] + n_hard * FLOP_PER_PATCH["hardnet"]
         tc_ms = sum(t for t, n, k in agg if k in TC_FAMILY)
         tc_launches = sum(n for t, n, k in agg if k in TC_FAMILY)
         ach = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-        roof = {"kernel": "tcgen05 kernels (%d launches/step: tc_first2_kernel x3, tc_conv_kernel x10, tc_conv_pair_kernel x2, tc_head_kernel, tc_headx_kernel x2; fp16 operands with fp16 "
-                          "residual planes for AffNet/OriNet, fp32 accumulate in TMEM)" % tc_launches,
+        roof = {"kernel": "tcgen05 kernels (%d launches/step: %s; fp16 operands with fp16 residual planes for AffNet/OriNet and HardNet layers 2-4, fp32 accumulate in TMEM)"
+                          % (tc_launches, ", ".join("%s x%d" % (k, n) for t, n, k in agg if k in TC_FAMILY)),
                 "bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"],
                 "traffic": ncu_traffic(B), "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)", "kernel_ms_per_step": tc_ms,
                 "algorithmic_flop_per_step": tc_flop, "share_of_step": tc_ms / step_ms if step_ms else None,
-                "note": "algorithmic flops = 2*MAC of the reference's fp32 convolutions; the residual-plane products (2-3 MMAs per K step for AffNet/OriNet), the "
-                        "rows of zero padding in every 128-row tile and the K=9 first layer padded to K=16 are extra tensor work that is not counted",
+                "note": "algorithmic flops = 2*MAC of the reference's fp32 convolutions; the residual-plane products (3 MMAs per K step for AffNet/OriNet, 2 for HardNet "
+                        "layers 2-4) and the K=9 first layer padded to K=16 are extra tensor work that is not counted",
                 "timing": "CUDA events after every launch over %d profiled steps right after the timed region" % prof_steps,
                 "stages_ms": {k: round(t, 4) for t, n, k in agg}, "launches_ms": order}
-        cnn_ms = sum(t for t, n, k in agg if k in TC_FAMILY + ("first_layer_kernel", "hardnet_head_kernel", "affnet_head_kernel", "orinet_head_kernel", "conv3x3_kernel"))
-        cnn_flop = n_aff * FLOP_PER_PATCH["affnet"] + n_ori * FLOP_PER_PATCH["orinet"] + n_hard * FLOP_PER_PATCH["hardnet"]
-        roof["cnn_all"] = {"kernels": "all CNN kernels (first layer, tc trunks, heads)", "ms_per_step": cnn_ms, "achieved": cnn_flop / (cnn_ms * 1e-3) / 1e12 if cnn_ms else None,
-                           "unit": "TFLOP/s", "algorithmic_flop_per_step": cnn_flop}
-        # HBM roofline of the stencil side (pyramid + detect kernels) and of the sampler, reported alongside
-        st_ms = sum(t for t, n, k in agg if k in ("blur_kernel", "detect_level_kernel", "detect_fused_kernel", "detect_warp_kernel", "resolve_kernel"))
-        roof["stencil"] = {"kernels": "blur_kernel x25 + detect_warp_kernel (fused Hessian/NMS/soft-argmax, 1 launch) + resolve_kernel", "bound": "hbm", "achieved": ALG_BYTES_PER_PX * B * H * W / (st_ms * 1e-3) / 1e9 if st_ms else None,
+        # HBM roofline of the stencil side (pyramid + detect kernels), reported alongside
+        st_ms = sum(t for t, n, k in agg if k in STENCIL)
+        roof["stencil"] = {"kernels": ", ".join("%s x%d" % (k, n) for t, n, k in agg if k in STENCIL), "bound": "hbm",
+                           "achieved": ALG_BYTES_PER_PX * B * H * W / (st_ms * 1e-3) / 1e9 if st_ms else None,
                            "peak": pk["hbm"], "unit": "GB/s", "ms_per_step": st_ms}
         if roof["stencil"]["achieved"]:
             roof["stencil"]["frac"] = roof["stencil"]["achieved"] / pk["hbm"]
-        sm_ms = sum(t for t, n, k in agg if k == "extract_patches_pyr_kernel")
-        if sm_ms:
-            sb = (n_aff + n_ori + n_hard) * 8192.0   # 8 KiB per patch per materialised pass
-            roof["sampler"] = {"kernels": "extract_patches_pyr_kernel x3", "bound": "hbm", "achieved": sb / (sm_ms * 1e-3) / 1e9, "peak": pk["hbm"],
-                               "unit": "GB/s", "ms_per_step": sm_ms, "frac": sb / (sm_ms * 1e-3) / 1e9 / pk["hbm"]}
+
+    launches_per_step = pipe.launches
+    extra = None
+    if not args.no_extras and args.config == "2" and not args.batch:
+        wl.close(); wl = None; pipe = None
+        extra = {}
+        plan = [("b1", "2", 1, 10), ("b64_config4_shard", "2", 64, 3)] if world > 1 else [("b1", "2", 1, 10), ("b64_config4_shard", "2", 64, 3), ("config3", "3", 64, 2), ("config5", "5", 1, 5)]
+        for name, cfg, b, st in plan:
+            try:
+                Hh, Ww, Kk, bb, _, lab = CONFIGS[cfg]
+                w2 = Workload(ctx, Hh, Ww, Kk, bb, b, use_graph)
+                extra[name] = w2.summary(st, 3, e2e=True)
+                extra[name]["config"] = lab
+                w2.close()
+            except Exception as e:   # noqa: BLE001  (an extra must never cost the headline line)
+                extra[name] = {"error": str(e)[:300]}
+            w2 = None
+            torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        threads = best_cpu_threads()
-        dt, m, kps = cpu_reference_leg(args.ref_images, threads)
-        cpu = {"value": m, "unit": "Mpix/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port", "kpatches_per_s": kps,
-               "sample": "%d of the %d images of one step, oracle/affnet_oracle.py, fastest torch thread count of a sweep (%.1f s)" % (args.ref_images, B, dt)}
+        threads = best_cpu_threads(H, W)
+        arm = CpuArm(H, W, K, border)
+        dt, m, kps = arm.leg(make_images(args.ref_images, 1234, H, W), threads)
+        cpu = {"value": m, "unit": "Mpix/s", "cores": threads, "host_cores": os.cpu_count(), "kind": arm.kind, "kpatches_per_s": kps,
+               "sample": "%d of the %d images of one step, %s, fastest torch thread count of a sweep (%.1f s)" % (args.ref_images, B, arm.what, dt)}
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -420,16 +516,18 @@ def _main(real_stdout):
         e2e_v = pix / (e2e_ms / args.steps * 1e-3) / 1e6
         line = {"metric": "Mpix/s end-to-end HesAffNet(+OriNet)+HardNet", "value": value, "unit": "Mpix/s",
                 "kpatches_per_s": world * n_desc / (ms_per_step * 1e-3) / 1e3, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
                 "data": "synthetic images (seeded noise, blur sigma 2, stretched), pretrained weights from tests/golden",
-                "config": {"workload": "%dx%d grayscale, %d kpts/img, batch of %d images per GPU per step (configs[1] tiled = configs[3] shard)" % (W, H, K, B),
-                           "do_ori": True, "border": 5, "mrSize": 5.192, "cuda_graph": use_graph, "l2": "256 MiB flush write between timed steps (device-resident leg); e2e leg: fresh inputs arrive by DMA every step, no flush",
+                "config": {"workload": "%dx%d grayscale, %d kpts/img, batch of %d images per GPU per step (%s)" % (W, H, K, B, label),
+                           "do_ori": True, "border": border, "mrSize": 5.192, "cuda_graph": use_graph, "l2": "256 MiB flush write between timed steps (device-resident leg); e2e leg: fresh inputs arrive by DMA every step, no flush",
                            "parallelism": "images sharded across GPUs, one NCCL all-gather of descriptors+LAFs+counts per step, overlapped with the next step's compute" if world > 1 else "single GPU"},
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "e2e": {"value": e2e_v, "unit": "Mpix/s", "h2d_bytes_per_step": B * H * W * 4,
                         "d2h_bytes_per_step": B * K * (128 + 6 + 1) * 4 + B * 4, "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": pipe.launches * args.steps, "launches_per_step": pipe.launches,
+                "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
                 "descriptors_per_step": world * n_desc}
+        if extra is not None:
+            line["extra"] = extra
         emit(real_stdout, line)
     if dist is not None:
         dist.destroy_process_group()

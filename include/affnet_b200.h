@@ -163,14 +163,19 @@ typedef struct ag_net ag_net_t;
 int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out);
 void ag_net_destroy(ag_net_t* net);
 size_t ag_net_blob_floats(int kind);
-/* Compute engine: 0 = exact fp32 SIMT (needs materialised patches); 1 = tcgen05 tensor cores: fp16 operands, fp32
- * accumulation in TMEM, all six conv layers and the 8x8 heads as MMAs; the first layer and the AffNet/OriNet heads carry fp16
- * residual planes of both operands, AffNet's layers 2-6 the residual of the weights, OriNet's the residuals of weights and
- * activations (measured error vs the fp32 reference: A 1.9e-4, angle 2.8e-5 rad, descriptors 5.8e-4); 2 = residuals of weights
- * and activations for AffNet too and fp32 FMA-chain heads (A 2e-6, angle 3e-6 rad; AffNet/OriNet only).
- * Default: 1 for all three nets. */
+/* Compute engine: 0 = exact fp32 SIMT (needs materialised patches); 1 = tcgen05 tensor cores (default for all three nets): fp16
+ * operands, fp32 accumulation in TMEM, all six conv layers and the 8x8 heads as MMAs; AffNet and OriNet carry fp16 residual
+ * planes of weights AND activations in every layer (fp32-grade: A 1e-5, angle 3e-5 rad - OriNet's atan2 amplifies an error of
+ * AffNet's A about 15x, so the 1e-3 LAF contract needs A to 5e-5), HardNet plain fp16 operands (descriptors 6e-4);
+ * 2 = as 1 with fp32 FMA-chain heads (A 2e-6, angle 3e-6 rad; AffNet/OriNet only); 3 = AffNet with the weight residual only
+ * (A 2e-4; for A/B timing, AffNet only);
+ * 4 = second-generation tcgen05 engine (same operand precision as 1, plus fp16 residuals of HardNet's layer 2-4 weights): 128-pixel
+ * row tiles without x padding, the three taps of a kernel row stacked along N of one MMA, x shifts by warp shuffles in the epilogue. */
 int ag_net_set_engine(ag_net_t* net, int engine);
 int ag_net_get_engine(const ag_net_t* net);
+/* Developer diagnostic: run the second-generation trunk on materialised patches [n,32,32] up to conv layer `upto` (2..5) and decode
+ * that layer's activations (fp16 hi [+ lo] planes in the engine's HBM layout) to fp32 [n,C,H,H].  d_ws: ag_net_workspace_bytes(). */
+int ag_debug_tcx_layer(const ag_net_t* net, const float* d_patches, int n, int upto, float* d_out, void* d_ws, size_t ws_bytes, void* stream);
 /* Scratch bytes for a forward over n patches. */
 size_t ag_net_workspace_bytes(int kind, int n);
 

@@ -1,5 +1,5 @@
-"""Harness that imports the UNMODIFIED reference (ducha-aiki/affnet) from $AFFNET_REF
-(default /root/reference) on CPU.  TEST INFRASTRUCTURE ONLY: used by
+"""Harness that imports the UNMODIFIED reference (ducha-aiki/affnet) from $AFFNET_REF, /root/reference or
+baseline/_ref (first that holds SparseImgRepresenter.py) on CPU.  TEST INFRASTRUCTURE ONLY: used by
 `tests/golden/make_golden.py` to generate golden vectors and by `-m "not gpu"` tests (when the
 reference tree is present) to pin `oracle/affnet_oracle.py`.  Never imported by the product.
 
@@ -15,7 +15,16 @@ import types
 import numpy as np
 import torch
 
-REF = os.environ.get("AFFNET_REF", "/root/reference")
+def _find_ref():
+    """Search order: $AFFNET_REF, /root/reference, baseline/_ref next to the repository."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for c in (os.environ.get("AFFNET_REF"), "/root/reference", os.path.join(here, "baseline", "_ref")):
+        if c and os.path.isfile(os.path.join(c, "SparseImgRepresenter.py")):
+            return c
+    return os.environ.get("AFFNET_REF", "/root/reference")
+
+
+REF = _find_ref()
 
 
 def available():

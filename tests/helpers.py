@@ -71,3 +71,24 @@ def parity_report(oL, odesc, dL, desc, tag=""):
 
 
 TOL = 1e-3     # north_star: LAF parameters (relative to the LAF scale) and HardNet descriptors within 1e-3
+
+
+def synthetic_image(H, W, seed):
+    """SURVEY.md §8(d) config 3 input: U[0,255) noise blurred with sigma=2 (separable, replicate border), stretched to 0..255.
+    Bit-identical to oracle/affnet_oracle.py::synthetic_image (tests/test_lib_cpu.py checks it); lives here so that bench.py's
+    product arm generates its inputs without importing the oracle."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(1, 1, H, W, generator=g) * 255.0
+    sigma = 2.0
+    k = int(2.0 * 3.0 * sigma + 1.0)
+    if k % 2 == 0:
+        k += 1
+    half = k / 2.0
+    xs = np.linspace(-half, half, k)
+    e = np.exp(-(xs * xs) / (2.0 * sigma * sigma))
+    k1 = torch.from_numpy((e / e.sum()).astype(np.float32))
+    x = F.conv2d(F.pad(x, (k // 2, k // 2, 0, 0), "replicate"), k1.view(1, 1, 1, k))
+    x = F.conv2d(F.pad(x, (0, 0, k // 2, k // 2), "replicate"), k1.view(1, 1, k, 1))
+    x = (x - x.min()) / (x.max() - x.min()) * 255.0
+    return x.contiguous()

@@ -201,8 +201,8 @@ def test_level_selection_identical(L):
 
 @pytest.mark.parametrize("engine", ["simt", "tc"])
 def test_nets_vs_oracle(L, nets, engine):
-    """a9/a12/a16.  simt = exact fp32 engine (1e-4); tc = tcgen05 engine (default), fp32 accumulate, fp32 first layer and
-    head: north_star's 1e-3 for A matrices, rotations/angles and descriptors."""
+    """a9/a12/a16.  simt = exact fp32 engine (1e-4); tc = first-generation tcgen05 engine (the default second-generation engine has
+    the same checks in tests/test_gpu_tcx.py): north_star's 1e-3 for descriptors, fp32-grade A matrices and angles."""
     aff, ori, hn = nets
     e = L.ENGINE_SIMT if engine == "simt" else L.ENGINE_TC
     z = gold("graf_crop.npz")
@@ -226,10 +226,11 @@ def test_nets_vs_oracle(L, nets, engine):
         if engine == "simt":
             assert max(worst) < 1e-4, worst
         else:
-            # tensor cores: HardNet fp16 operands; AffNet + fp16 weight residual; OriNet + weight and activation residuals
-            assert worst[3] < 1e-3 and worst[0] < 1e-3 and worst[1] < 1e-3 and worst[2] < 1e-3, worst
+            # tensor cores: HardNet fp16 operands (1e-3); AffNet / OriNet weight and activation residuals (fp32-grade: the LAF
+            # contract needs A to 5e-5 because OriNet's atan2 amplifies an error of A about 15x)
+            assert worst[3] < 1e-3 and worst[0] < 5e-5 and worst[1] < 1e-4 and worst[2] < 1e-4, worst
     finally:
-        aff.set_engine(L.ENGINE_TC); ori.set_engine(L.ENGINE_TC); hn.set_engine(L.ENGINE_TC)
+        aff.set_engine(L.ENGINE_TC2); ori.set_engine(L.ENGINE_TC2); hn.set_engine(L.ENGINE_TC2)
     assert aff(torch.empty(0, 1, 32, 32, device=DEV)).shape == (0, 2, 2)
     if engine == "tc":   # exact tensor-core engine for AffNet: fp32-grade A
         try:
@@ -242,7 +243,7 @@ def test_nets_vs_oracle(L, nets, engine):
             print("engine tc-exact: max|dA| %.2e  max|dangle| %.2e rad" % (dA, dang))
             assert dA < 2e-5 and dang < 1e-4
         finally:
-            aff.set_engine(L.ENGINE_TC); ori.set_engine(L.ENGINE_TC)
+            aff.set_engine(L.ENGINE_TC2); ori.set_engine(L.ENGINE_TC2)
 
 
 def test_nets_batching_invariance(L, nets):

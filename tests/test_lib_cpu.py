@@ -127,3 +127,11 @@ def test_host_lafs2ell_matches_reference_golden():
     assert np.array_equal(e[:, :2], g[:, :2])
     assert np.allclose(e[:, 2:], g[:, 2:], rtol=1e-6, atol=0)       # same float32 SVD as the reference (LAPACK build may differ in the last bit)
     assert LAFs2ell(np.zeros((0, 2, 3))).shape == (0, 5)
+
+
+def test_helpers_synthetic_image_is_the_oracles():
+    """bench.py's product arm takes its inputs from tests/helpers.py so that it imports nothing from oracle/: same bits as the oracle's generator."""
+    import torch
+    import affnet_oracle as O
+    from helpers import synthetic_image
+    assert torch.equal(synthetic_image(96, 131, 7), O.synthetic_image(96, 131, 7))
