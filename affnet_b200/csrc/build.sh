@@ -27,3 +27,9 @@ if [ "${AG_ROLE_PROF:-0}" = "1" ]; then mkdir -p "$HERE/obj_prof";   # developer
   $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libaffnet_b200_prof.so" $objs "$HERE/obj_prof/nets_tc.o" -lcudart
   echo "built $OUT/libaffnet_b200_prof.so"
 fi
+if [ "${AG_XPROF:-0}" = "1" ]; then mkdir -p "$HERE/obj_prof";   # developer build with the warp-role cycle counters of the second-generation engine (scripts/role_prof_x.py)
+  $NVCC $FLAGS -DAG_ROLE_PROF -c "$HERE/nets_tcx.cu" -o "$HERE/obj_prof/nets_tcx.o" > "$HERE/obj_prof/nets_tcx.log" 2>&1 || { cat "$HERE/obj_prof/nets_tcx.log"; exit 1; }
+  objs=$(ls "$HERE"/obj/*.o | grep -v nets_tcx.o)
+  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libaffnet_b200_xprof.so" $objs "$HERE/obj_prof/nets_tcx.o" -lcudart
+  echo "built $OUT/libaffnet_b200_xprof.so"
+fi

@@ -40,13 +40,14 @@ static int ensure_smem_attr(const void* func, int bytes, bool* configured, const
 
 template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW>
 static int launch_conv(const void* in, void* out, const __half* w, const float* b, float inv_scale, int n, int group, const int* count, cudaStream_t st) {
+    constexpr int prof_id = (H == 32) ? 2 : (H == 16 ? (STRIDE == 1 ? 3 : 4) : 5);
     using Cfg = XCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW>;
     auto kern = tcx_conv_kernel<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW>;
     static bool configured[64] = {};   // per device (the attribute is per device)
     int rc = ensure_smem_attr((const void*)kern, (int)Cfg::SMEM, configured, "tcx_conv smem attr");
     if (rc != AG_OK) return rc;
     XArgs a;
-    a.in = (const __half*)in; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.n = n; a.group = group; a.count = count;
+    a.in = (const __half*)in; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.n = n; a.group = group; a.count = count; a.prof_id = prof_id;
     const int units = Cfg::In::PAIR ? (n + 1) / 2 : n;
     int gx = num_sms() / NSPLIT;
     if (gx > units) gx = units;
@@ -64,7 +65,7 @@ static int launch_first(void* out, const __half* w, const float* b, float inv_sc
     int rc = ensure_smem_attr((const void*)kern, (int)Cfg::SMEM, configured, "tcx_first smem attr");
     if (rc != AG_OK) return rc;
     XArgs a;
-    a.in = nullptr; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.n = n; a.group = group; a.count = count;
+    a.in = nullptr; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.n = n; a.group = group; a.count = count; a.prof_id = 0;
     int gx = num_sms();
     if (gx > n) gx = n;
     if (gx < 1) gx = 1;
@@ -201,3 +202,12 @@ int ag_debug_tcx_layer(const ag_net_t* net, const float* d_patches, int n, int u
 }
 
 }  // extern "C"
+
+#ifdef AG_ROLE_PROF
+// developer-only: per-CTA role cycle counters of the last second-generation launches (tcx_conv.cuh)
+extern "C" int ag_debug_role_prof_x(unsigned long long* out) {
+    if (cudaMemcpyFromSymbol(out, ag::tcx::g_xprof, sizeof(unsigned long long) * 8 * 160 * 20) != cudaSuccess) return 1;
+    void* p = nullptr;
+    return (cudaGetSymbolAddress(&p, ag::tcx::g_xprof) == cudaSuccess && cudaMemset(p, 0, sizeof(unsigned long long) * 8 * 160 * 20) == cudaSuccess) ? 0 : 1;
+}
+#endif

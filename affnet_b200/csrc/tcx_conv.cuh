@@ -35,6 +35,15 @@ namespace tcx {
 
 using namespace ag::tc;
 
+// Developer-only role profiler (scripts/role_prof_x.py, build with AG_XPROF=1): cycles of one warp of every role and its barrier waits.
+#ifdef AG_ROLE_PROF
+__device__ unsigned long long g_xprof[8][160][20];   // [slot: 0 tcx_first, l = conv layer l+1][CTA][role*5 + k]
+#define XP_STORE(slot, role) do { if (lane == 0) { unsigned long long* d_ = g_xprof[slot][blockIdx.x + gridDim.x * blockIdx.y] + (role) * 5; \
+    d_[0] = clock64() - rp_t0; d_[1] = rp_w[0]; d_[2] = rp_w[1]; d_[3] = rp_w[2]; d_[4] = rp_w[3]; } } while (0)
+#else
+#define XP_STORE(slot, role)
+#endif
+
 enum XLayout { L_S2_16 = 0, L_S1_16 = 1, L_S2_8P = 2, L_S1_8P = 3, L_HEAD = 4 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -78,6 +87,7 @@ struct XArgs {
     const float* bias;    // [COUT]
     float inv_scale;      // 1 / (power-of-two scale of wpk)
     int n, group;         // patches, patches per image
+    int prof_id;          // developer role profiler slot
     const int* count;     // valid patches per image (NULL: all)
 };
 
@@ -157,10 +167,11 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
             mbar_expect_tx(wbar, Cfg::W_BYTES);
             bulk_g2s(sW, reinterpret_cast<const unsigned char*>(a.wpk) + (size_t)split * Cfg::W_BYTES, Cfg::W_BYTES, wbar);
             int it = 0;
+            RP_DECL;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 if (!uvalid(u)) continue;
                 const int s = it % STAGES;
-                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                RP_WAIT(0, mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1));
                 mbar_expect_tx(&full[s], Cfg::UNIT_IN_BYTES);
                 const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.in) + (size_t)u * Cfg::UNIT_IN_BYTES;
 #pragma unroll 1
@@ -171,6 +182,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
                                  gsrc + ((size_t)g * In::NPLANES + pl) * In::DATA * 16, In::DATA * 16u, &full[s]);
                 it++;
             }
+            XP_STORE(a.prof_id, 3);
         }
     } else if (warp == 1) {
         // ===== MMA issuer (warp-uniform control flow, one elected lane issues) =====
@@ -184,16 +196,17 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
         const uint32_t in_base = smem_u32(sIn) >> 4;
         constexpr uint32_t LBO_A = ((uint32_t)GS) << 16;      // (bytes >> 4) << 16
         int it = 0, tcnt = 0;
+        RP_DECL;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             if (!uvalid(u)) continue;
             const int s = it % STAGES;
-            mbar_wait(&full[s], (it / STAGES) & 1);
+            RP_WAIT(0, mbar_wait(&full[s], (it / STAGES) & 1));
             tc_fence_after();
             const uint32_t st_base = in_base + (uint32_t)(s * In::SLOT_STAGE);
 #pragma unroll 1
             for (int t = 0; t < TILES; t++, tcnt++) {
                 const int ab = tcnt % NACC;
-                mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1);
+                RP_WAIT(1, mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1));
                 tc_fence_after();
                 if (leader) {
                     const uint32_t d = tmem + (uint32_t)(ab * Cfg::ACCW);
@@ -247,6 +260,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
             __syncwarp();
             it++;
         }
+        XP_STORE(a.prof_id, 0);
     } else {
         // ===== epilogue: EW / 4 sets of four warps (TMEM lane quadrant = warp % 4), set k takes tiles k, k + NSETS, ... =====
         constexpr int NSETS = EW / 4;
@@ -254,13 +268,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
         const int set = (warp - 2) >> 2;
         const int r = q * 32 + lane;                         // tile row of this thread
         int tcnt = 0;
+        RP_DECL;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             if (!uvalid(u)) continue;
 #pragma unroll 1
             for (int t = 0; t < TILES; t++, tcnt++) {
                 if ((tcnt % NSETS) != set) continue;
                 const int ab = tcnt % NACC;
-                mbar_wait(&tfull[ab], (tcnt / NACC) & 1);
+                RP_WAIT(0, mbar_wait(&tfull[ab], (tcnt / NACC) & 1));
                 tc_fence_after();
                 // pixel of this row
                 int y, x, p, pi;
@@ -326,6 +341,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
                 }
             }
         }
+        if (warp == 2) XP_STORE(a.prof_id, 1);
     }
     tc_fence_before();
     __syncthreads();

@@ -131,9 +131,10 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
         const uint32_t p_lo = desc_lo(smem_u32(sP), 2 * 32 * 16u);          // leading-byte offset = two image rows
         constexpr uint32_t LBO_A = ((uint32_t)GS) << 16;
         int c1cnt = 0, tcnt = 0;
+        RP_DECL;
         auto l1_tile = [&](int t) {
             const int b = c1cnt % NL1;
-            mbar_wait(&c1_empty[b], ((c1cnt / NL1) & 1) ^ 1);
+            RP_WAIT(1, mbar_wait(&c1_empty[b], ((c1cnt / NL1) & 1) ^ 1));
             tc_fence_after();
             if (leader) {
                 const uint32_t d = tmem + (uint32_t)(b * Cfg::ACC1);
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
         };
         auto l2_tile = [&](uint32_t st_base, int t) {
             const int ab = tcnt % NACC;
-            mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1);
+            RP_WAIT(3, mbar_wait(&tempty[ab], ((tcnt / NACC) & 1) ^ 1));
             tc_fence_after();
             if (leader) {
                 const uint32_t d = tmem_l2 + (uint32_t)(ab * Cfg::ACCW);
@@ -197,8 +198,8 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
             const int pn = next_valid(pi + gridDim.x);
             const bool has_next = pn < a.n;
             const int s = it & 1;
-            if (has_next) { mbar_wait(p_full, (it + 1) & 1); tc_fence_after(); }
-            mbar_wait(&full[s], (it >> 1) & 1);
+            if (has_next) { RP_WAIT(0, mbar_wait(p_full, (it + 1) & 1)); tc_fence_after(); }
+            RP_WAIT(2, mbar_wait(&full[s], (it >> 1) & 1));
             tc_fence_after();
             const uint32_t st_base = in_base + (uint32_t)(s * Cfg::SLOT_STAGE);
 #pragma unroll 1
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
             it++;
             pi = pn;
         }
+        XP_STORE(0, 0);
     } else if (warp >= 4 && warp < 12) {
         // ===== layer-2 epilogue: TMEM -> x shifts -> bias + ReLU -> fp16 -> global (parity planes of the stride-2 consumer) =====
         const int q = warp & 3, set = (warp - 4) >> 2;
@@ -221,13 +223,14 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
         const int x = lane;
         const bool has_l = x > 0, has_r = x < 31;
         int tcnt = 0;
+        RP_DECL;
         for (int pi = next_valid(blockIdx.x); pi < a.n; pi = next_valid(pi + gridDim.x)) {
             unsigned char* outp = reinterpret_cast<unsigned char*>(a.out) + (size_t)pi * Cfg::UNIT_OUT_BYTES;
 #pragma unroll 1
             for (int t = 0; t < TILES; t++, tcnt++) {
                 if ((tcnt & 1) != set) continue;
                 const int ab = tcnt % NACC;
-                mbar_wait(&tfull[ab], (tcnt / NACC) & 1);
+                RP_WAIT(0, mbar_wait(&tfull[ab], (tcnt / NACC) & 1));
                 tc_fence_after();
                 const int y = t * 4 + q;
                 const uint32_t taddr = tmem_l2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACCW);
@@ -287,18 +290,20 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
                 }
             }
         }
+        if (warp == 4) XP_STORE(0, 1);
     } else if (warp >= 12 && warp < 16) {
         // ===== layer-1 epilogue: TMEM -> bias + ReLU -> fp16 (hi [+lo]) -> shared-memory stage of layer 2 =====
         const int q = warp & 3;
         int it = 0, c1cnt = 0;
+        RP_DECL;
         for (int pi = next_valid(blockIdx.x); pi < a.n; pi = next_valid(pi + gridDim.x), it++) {
             const int s = it & 1;
-            mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+            RP_WAIT(0, mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1));
             unsigned char* st = sIn + (size_t)s * Cfg::SLOT_STAGE * 16;
 #pragma unroll 1
             for (int t = 0; t < TILES; t++, c1cnt++) {
                 const int b = c1cnt % NL1;
-                mbar_wait(&c1_full[b], (c1cnt / NL1) & 1);
+                RP_WAIT(1, mbar_wait(&c1_full[b], (c1cnt / NL1) & 1));
                 tc_fence_after();
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * Cfg::ACC1);
                 uint32_t r[32];
@@ -332,6 +337,7 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&full[s]);
         }
+        if (warp == 12) XP_STORE(0, 2);
     } else if (warp < 4 || warp >= 16) {
         // ===== producers (8 warps): sampler (or patch load) -> input_norm -> sliding-window planes P_hi / P_lo =====
         const int pw = warp < 4 ? warp - 1 : warp - 13;      // 0..7
@@ -362,6 +368,7 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
         int pi = next_valid(blockIdx.x);
         if (pi < a.n) issue_fetch(pi);
         int it = 0;
+        RP_DECL;
         while (pi < a.n) {
             float* sx = s_x + (it & 1) * SX;
             float* red = s_red + (it & 1) * 16;
@@ -386,7 +393,7 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
 #pragma unroll
             for (int k = 0; k < 4; k++) { const int p = pix_of(k); sx[((p >> 5) + 1) * 34 + (p & 31) + 1] = (v[k] - mean) * inv; }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            mbar_wait(p_empty, (it & 1) ^ 1);   // layer-1 MMAs of the previous patch have consumed the planes
+            RP_WAIT(0, mbar_wait(p_empty, (it & 1) ^ 1));   // layer-1 MMAs of the previous patch have consumed the planes
 #pragma unroll 1
             for (int s0 = pt; s0 < NPIXP; s0 += 256) {
                 const int base = (s0 >> 5) * 34 + (s0 & 31);
@@ -408,6 +415,7 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
             it++;
             pi = pn;
         }
+        if (warp == 1) XP_STORE(0, 3);
     }
     tc_fence_before();
     __syncthreads();
