@@ -69,7 +69,6 @@ class ScaleSpaceAffinePatchExtractor(nn.Module):
             L.check(lib.ag_detect_ws_carve(C.byref(plan), cap, L.ptr(ws_buf), C.byref(ws)))
             L.check(lib.ag_detect(C.byref(plan), L.ptr(self._pyr_buf), float(self.th), int(self.mrSize), C.byref(ws), L.stream_ptr()))
             n_slots = ws.n_level_slots
-            counters = torch.empty(0)
             if num_features > 0:
                 out_cap = num_features
                 resp = torch.empty(out_cap, dtype=torch.float32, device=dev)
@@ -149,12 +148,19 @@ class ScaleSpaceAffinePatchExtractor(nn.Module):
         lvl = final_level_idxs.to(torch.int32).contiguous()
         base_A = None
         cur = LAFs
+        lib = L.lib()
         for i in range(self.num_Baum_iters):
             patches = self._patches(cur, oct_, lvl, self.AffNet.PS)
-            A = self.AffNet(patches)
-            base_A = A if base_A is None else torch.bmm(A, base_A)
-            if i != self.num_Baum_iters - 1:
-                cur = torch.cat([torch.bmm(base_A, LAFs[:, :, 0:2]), LAFs[:, :, 2:]], dim=2)
+            A = L.f32c(self.AffNet(patches))
+            if base_A is None:
+                base_A = A
+            elif n:
+                nb = torch.empty_like(A)
+                L.check(lib.ag_mat2_compose(L.ptr(A), L.ptr(L.f32c(base_A)), L.ptr(nb), n, L.stream_ptr()))      # base_A <- A base_A (:133)
+                base_A = nb
+            if i != self.num_Baum_iters - 1 and n:
+                cur = torch.empty_like(LAFs)
+                L.check(lib.ag_lafs_left_multiply(L.ptr(L.f32c(base_A)), L.ptr(LAFs), L.ptr(cur), n, L.stream_ptr()))   # (:134-135)
         if base_A is None:
             base_A = torch.eye(2, device=dev).unsqueeze(0).expand(n, 2, 2)
         base_A = L.f32c(base_A)

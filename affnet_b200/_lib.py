@@ -75,6 +75,10 @@ PROTOTYPES = {
     "ag_net_set_engine": (i32, [vp, i32]),
     "ag_net_get_engine": (i32, [vp]),
     "ag_net_workspace_bytes": (sz, [i32, i32]),
+    "ag_mat2_compose": (i32, [vp, vp, vp, i32, vp]),
+    "ag_lafs_left_multiply": (i32, [vp, vp, vp, i32, vp]),
+    "ag_affnet_forward_raw": (i32, [vp, vp, i32, vp, vp, sz, vp]),
+    "ag_orinet_forward_raw": (i32, [vp, vp, i32, vp, vp, sz, vp]),
     "ag_debug_tcx_layer": (i32, [vp, vp, i32, i32, vp, vp, sz, vp]),
     "ag_affnet_forward": (i32, [vp, vp, i32, vp, i32, vp, vp, sz, vp]),
     "ag_orinet_forward": (i32, [vp, vp, i32, vp, i32, vp, vp, vp, sz, vp]),

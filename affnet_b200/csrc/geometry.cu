@@ -168,6 +168,28 @@ __global__ void lafs_to_ell_kernel(const float* __restrict__ lafs, float* __rest
 
 using namespace ag;
 
+namespace ag {
+// out = A * B for [n,2,2] batches, in torch.bmm's fp32 operation order (row-by-column, two products added left to right): the Baumberg
+// chain base_A <- A base_A of SparseImgRepresenter.py:133
+__global__ void mat2_compose_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a0 = A[i * 4], a1 = A[i * 4 + 1], a2 = A[i * 4 + 2], a3 = A[i * 4 + 3];
+    const float b0 = B[i * 4], b1 = B[i * 4 + 1], b2 = B[i * 4 + 2], b3 = B[i * 4 + 3];
+    out[i * 4 + 0] = __fmaf_rn(a1, b2, __fmul_rn(a0, b0)); out[i * 4 + 1] = __fmaf_rn(a1, b3, __fmul_rn(a0, b1));
+    out[i * 4 + 2] = __fmaf_rn(a3, b2, __fmul_rn(a2, b0)); out[i * 4 + 3] = __fmaf_rn(a3, b3, __fmul_rn(a2, b1));
+}
+// out = [A * L[:, :, :2] | L[:, :, 2]] : the working LAF of the next Baumberg iteration (SparseImgRepresenter.py:134-135)
+__global__ void lafs_left_multiply_kernel(const float* __restrict__ A, const float* __restrict__ Lf, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a0 = A[i * 4], a1 = A[i * 4 + 1], a2 = A[i * 4 + 2], a3 = A[i * 4 + 3];
+    const float l0 = Lf[i * 6], l1 = Lf[i * 6 + 1], l3 = Lf[i * 6 + 3], l4 = Lf[i * 6 + 4];
+    out[i * 6 + 0] = __fmaf_rn(a1, l3, __fmul_rn(a0, l0)); out[i * 6 + 1] = __fmaf_rn(a1, l4, __fmul_rn(a0, l1)); out[i * 6 + 2] = Lf[i * 6 + 2];
+    out[i * 6 + 3] = __fmaf_rn(a3, l3, __fmul_rn(a2, l0)); out[i * 6 + 4] = __fmaf_rn(a3, l4, __fmul_rn(a2, l1)); out[i * 6 + 5] = Lf[i * 6 + 5];
+}
+}  // namespace ag
+
 extern "C" {
 
 int ag_affine_shape_filter(const float* d_A, const float* d_resp, const float* d_lafs, const int* d_oct, const int* d_lvl,
@@ -203,6 +225,22 @@ int ag_lafs_apply_rotation(float* d_lafs, const float* d_R, int n, void* stream)
     if (n <= 0) return AG_OK;
     lafs_rotate_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d_lafs, d_R, n);
     AG_CHECK_LAUNCH("lafs_rotate_kernel");
+    return AG_OK;
+}
+
+int ag_mat2_compose(const float* d_A, const float* d_B, float* d_out, int n, void* stream) {
+    AG_REQUIRE(d_A && d_B && d_out, "NULL argument");
+    if (n <= 0) return AG_OK;
+    mat2_compose_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d_A, d_B, d_out, n);
+    AG_CHECK_LAUNCH("mat2_compose_kernel");
+    return AG_OK;
+}
+
+int ag_lafs_left_multiply(const float* d_A, const float* d_lafs, float* d_out, int n, void* stream) {
+    AG_REQUIRE(d_A && d_lafs && d_out, "NULL argument");
+    if (n <= 0) return AG_OK;
+    lafs_left_multiply_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d_A, d_lafs, d_out, n);
+    AG_CHECK_LAUNCH("lafs_left_multiply_kernel");
     return AG_OK;
 }
 

@@ -46,7 +46,7 @@ int tc_trunk_orinet(const ag_net* net, const tc::FirstSrc& src, int n, int group
                     cudaStream_t st);
 int tc_trunk_affnet(const ag_net* net, const tc::FirstSrc& src, int n, int group, const int* count, void* bufA, void* bufB, void* feat,
                     cudaStream_t st);
-int tc_headx_forward(const ag_net* net, const void* feat, int n, int group, const int* count, float* out, float* angle, cudaStream_t st);
+int tc_headx_forward(const ag_net* net, const void* feat, int n, int group, const int* count, float* out, float* angle, cudaStream_t st, float* raw = nullptr);
 size_t tc_headx_bytes(int n);
 // second-generation engine (nets_tcx.cu)
 void tcx_pack_layer(const float* wf, int ci, int co, int stride, int nsplit, int sw, float scale, std::vector<__half>& out);

@@ -581,8 +581,8 @@ static int split_ws(int kind, int n, void* d_ws, size_t ws_bytes, float** a, flo
 extern "C" {
 
 static int affnet_impl(const ag_net_t* net, const float* d_patches, const tc::FirstSrc* src, int n, const int* d_count, int group,
-                       float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
-    AG_REQUIRE(net && (d_patches || src) && d_out, "NULL argument");
+                       float* d_out, void* d_ws, size_t ws_bytes, void* stream, float* d_raw = nullptr) {
+    AG_REQUIRE(net && (d_patches || src) && (d_out || d_raw), "NULL argument");
     AG_REQUIRE(net->kind == AG_NET_AFFNET, "not an AffNet handle");
     if (n <= 0) return AG_OK;
     if (group <= 0) group = n;
@@ -591,15 +591,16 @@ static int affnet_impl(const ag_net_t* net, const float* d_patches, const tc::Fi
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = run_trunk(net, d_patches, src, n, group, d_count, a, b, &b, st))) return rc;
-    if (net->engine == AG_ENGINE_TC || net->engine == AG_ENGINE_TC_FAST || net->engine == AG_ENGINE_TC2) return tc_headx_forward(net, b, n, group, d_count, d_out, nullptr, st);
+    if (net->engine == AG_ENGINE_TC || net->engine == AG_ENGINE_TC_FAST || net->engine == AG_ENGINE_TC2) return tc_headx_forward(net, b, n, group, d_count, d_out, nullptr, st, d_raw);
+    AG_REQUIRE(d_raw == nullptr && d_out, "raw head outputs need a tensor-core engine with the GEMM head (1, 3 or 4)");
     affnet_head_kernel<<<cdiv(n, 8), 256, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, n, group, d_count);
     AG_CHECK_LAUNCH("affnet_head_kernel");
     return AG_OK;
 }
 
 static int orinet_impl(const ag_net_t* net, const float* d_patches, const tc::FirstSrc* src, int n, const int* d_count, int group,
-                       float* d_out, float* d_angle, void* d_ws, size_t ws_bytes, void* stream) {
-    AG_REQUIRE(net && (d_patches || src) && (d_out || d_angle), "NULL argument");
+                       float* d_out, float* d_angle, void* d_ws, size_t ws_bytes, void* stream, float* d_raw = nullptr) {
+    AG_REQUIRE(net && (d_patches || src) && (d_out || d_angle || d_raw), "NULL argument");
     AG_REQUIRE(net->kind == AG_NET_ORINET, "not an OriNet handle");
     if (n <= 0) return AG_OK;
     if (group <= 0) group = n;
@@ -608,7 +609,8 @@ static int orinet_impl(const ag_net_t* net, const float* d_patches, const tc::Fi
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = run_trunk(net, d_patches, src, n, group, d_count, a, b, &b, st))) return rc;
-    if (net->engine == AG_ENGINE_TC || net->engine == AG_ENGINE_TC2) return tc_headx_forward(net, b, n, group, d_count, d_out, d_angle, st);
+    if (net->engine == AG_ENGINE_TC || net->engine == AG_ENGINE_TC2) return tc_headx_forward(net, b, n, group, d_count, d_out, d_angle, st, d_raw);
+    AG_REQUIRE(d_raw == nullptr, "raw head outputs need a tensor-core engine with the GEMM head (1 or 4)");
     orinet_head_kernel<<<cdiv(n, OH_W * OH_P), OH_W * 32, 0, st>>>(b, net->d_head_w, net->d_head_b, d_out, d_angle, n, group, d_count);
     AG_CHECK_LAUNCH("orinet_head_kernel");
     return AG_OK;
@@ -652,6 +654,15 @@ int ag_orinet_forward(const ag_net_t* net, const float* d_patches, int n, const 
                       void* d_ws, size_t ws_bytes, void* stream) {
     AG_REQUIRE(d_patches, "NULL patches");
     return orinet_impl(net, d_patches, nullptr, n, d_count, group, d_out, d_angle, d_ws, ws_bytes, stream);
+}
+/* Raw head outputs, the TorchScript modules' contract (convertJIT/AffNetJIT.pt: xy + [1, 0, 1] -> [n,3]; OriNetJIT.pt: xy -> [n,2]). */
+int ag_affnet_forward_raw(const ag_net_t* net, const float* d_patches, int n, float* d_raw, void* d_ws, size_t ws_bytes, void* stream) {
+    AG_REQUIRE(d_patches && d_raw, "NULL argument");
+    return affnet_impl(net, d_patches, nullptr, n, nullptr, n, nullptr, d_ws, ws_bytes, stream, d_raw);
+}
+int ag_orinet_forward_raw(const ag_net_t* net, const float* d_patches, int n, float* d_raw, void* d_ws, size_t ws_bytes, void* stream) {
+    AG_REQUIRE(d_patches && d_raw, "NULL argument");
+    return orinet_impl(net, d_patches, nullptr, n, nullptr, n, nullptr, nullptr, d_ws, ws_bytes, stream, d_raw);
 }
 int ag_hardnet_forward(const ag_net_t* net, const float* d_patches, int n, const int* d_count, int group, float* d_out, void* d_ws,
                        size_t ws_bytes, void* stream) {

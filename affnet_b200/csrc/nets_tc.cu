@@ -214,7 +214,7 @@ int tc_trunk_orinet(const ag_net* net, const tc::FirstSrc& src0, int n, int grou
 }
 
 // AffNet / OriNet head on tensor cores over the hi/lo feature planes the trunks above leave in `feat`
-int tc_headx_forward(const ag_net* net, const void* feat, int n, int group, const int* count, float* out, float* angle, cudaStream_t st) {
+int tc_headx_forward(const ag_net* net, const void* feat, int n, int group, const int* count, float* out, float* angle, cudaStream_t st, float* raw) {
     using namespace tc;
     static bool configured = false;
     if (!configured) {
@@ -224,8 +224,8 @@ int tc_headx_forward(const ag_net* net, const void* feat, int n, int group, cons
         configured = true;
     }
     const int tiles = (n + 127) / 128;
-    if (net->kind == AG_NET_AFFNET) tc_headx_kernel<0><<<tiles, 192, HX_SMEM, st>>>((const __half*)feat, net->d_headh, net->d_head_b, net->head_inv_scale, out, nullptr, n, group, count);
-    else tc_headx_kernel<1><<<tiles, 192, HX_SMEM, st>>>((const __half*)feat, net->d_headh, net->d_head_b, net->head_inv_scale, out, angle, n, group, count);
+    if (net->kind == AG_NET_AFFNET) tc_headx_kernel<0><<<tiles, 192, HX_SMEM, st>>>((const __half*)feat, net->d_headh, net->d_head_b, net->head_inv_scale, out, nullptr, raw, n, group, count);
+    else tc_headx_kernel<1><<<tiles, 192, HX_SMEM, st>>>((const __half*)feat, net->d_headh, net->d_head_b, net->head_inv_scale, out, angle, raw, n, group, count);
     AG_CHECK_LAUNCH("tc_headx_kernel");
     return AG_OK;
 }

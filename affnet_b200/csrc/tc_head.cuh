@@ -135,7 +135,7 @@ constexpr size_t HX_PLANE_TILE = (size_t)(HX_K / 8) * 128 * 16;   // bytes of on
 
 template <int KIND /* 0 AffNet, 1 OriNet */>
 __global__ void __launch_bounds__(192, 1) tc_headx_kernel(const __half* __restrict__ feat, const __half* __restrict__ wh, const float* __restrict__ bias,
-                                                           const float inv_scale, float* __restrict__ out, float* __restrict__ angle_out, int n, int group,
+                                                           const float inv_scale, float* __restrict__ out, float* __restrict__ angle_out, float* __restrict__ raw_out, int n, int group,
                                                            const int* __restrict__ count) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -230,11 +230,14 @@ __global__ void __launch_bounds__(192, 1) tc_headx_kernel(const __half* __restri
             if (KIND == 0) {
                 const float s0 = acc[0] * inv_scale, s1 = acc[1] * inv_scale, s2 = acc[2 % NO] * inv_scale;
                 const float a00 = 1.0f + tanhf(s0 + bias[0]), a01 = 0.f, a10 = tanhf(s1 + bias[1]), a11 = 1.0f + tanhf(s2 + bias[2]);
-                const float det = sqrtf(fabsf(a00 * a11 - a10 * a01 + 1e-10f));
-                const float b2a2 = sqrtf(a01 * a01 + a00 * a00);
-                float* o = out + (size_t)pi * 4;
-                o[0] = b2a2 / det; o[1] = 0.f;
-                o[2] = (a11 * a01 + a10 * a00) / (b2a2 * det); o[3] = det / b2a2;
+                if (raw_out) { raw_out[(size_t)pi * 3] = a00; raw_out[(size_t)pi * 3 + 1] = a10; raw_out[(size_t)pi * 3 + 2] = a11; }   // convertJIT/AffNetJIT.pt: xy + [1, 0, 1]
+                if (out) {
+                    const float det = sqrtf(fabsf(a00 * a11 - a10 * a01 + 1e-10f));
+                    const float b2a2 = sqrtf(a01 * a01 + a00 * a00);
+                    float* o = out + (size_t)pi * 4;
+                    o[0] = b2a2 / det; o[1] = 0.f;
+                    o[2] = (a11 * a01 + a10 * a00) / (b2a2 * det); o[3] = det / b2a2;
+                }
             } else {
                 float m0 = 0.f, m1 = 0.f;
 #pragma unroll
@@ -243,6 +246,7 @@ __global__ void __launch_bounds__(192, 1) tc_headx_kernel(const __half* __restri
                     m1 += tanhf(acc[(9 + o) % NO] * inv_scale + bias[1]);
                 }
                 m0 /= 9.0f; m1 /= 9.0f;
+                if (raw_out) { raw_out[(size_t)pi * 2] = m0; raw_out[(size_t)pi * 2 + 1] = m1; }   // convertJIT/OriNetJIT.pt: the mean of tanh over the 3x3 map
                 const float ang = atan2f(m0 + 1e-8f, m1 + 1e-8f);
                 if (angle_out) angle_out[pi] = ang;
                 if (out) {

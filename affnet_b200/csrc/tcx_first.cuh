@@ -28,7 +28,10 @@ struct XFirstCfg {
     static constexpr int S1 = (C1 == 16) ? 1 : 0;              // layer 1: x_hi * [w_hi ; w_lo] as one N = 2*C1 MMA
     static constexpr int ACC1 = 32;                            // layer-1 accumulator columns per tile (2*16 stacked, or 32)
     static constexpr int NL1 = 4;                              // layer-1 accumulator buffers
-    static constexpr int STACK = (SW && 6 * NT <= 96) ? 1 : 0; // layer 2: [W_hi ; W_lo] stacked along N
+#ifndef AG_FIRST_STACK
+#define AG_FIRST_STACK 0   // the kernel is bound by SIMT instruction issue, not by the tensor pipe: the extra hi + lo adds of the stacked form cost more than its MMAs save
+#endif
+    static constexpr int STACK = (AG_FIRST_STACK && SW && 6 * NT <= 96) ? 1 : 0; // layer 2: [W_hi ; W_lo] stacked along N
     static constexpr int ACCW = 3 * NT * (1 + STACK);
     static constexpr int NACC = (512 - NL1 * ACC1) / ACCW < 4 ? (512 - NL1 * ACC1) / ACCW : 4;
     static constexpr int G = KC * (1 + SA);
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
         const int q = warp & 3, set = (warp - 4) >> 2;
         const int r = q * 32 + lane;
         const int x = lane;
-        const bool has_l = x > 0, has_r = x < 31;
+        const float mask_l = x > 0 ? 1.f : 0.f, mask_r = x < 31 ? 1.f : 0.f;
         int tcnt = 0;
         RP_DECL;
         for (int pi = next_valid(blockIdx.x); pi < a.n; pi = next_valid(pi + gridDim.x)) {
@@ -269,23 +272,16 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
                     for (int i = 0; i < 16; i++) {
                         const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[i]), 1);
                         const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[i]), 1);
-                        const float acc = __uint_as_float(r1[i]) + ((has_l ? left : 0.f) + (has_r ? right : 0.f));
+                        const float acc = fmaf(left, mask_l, fmaf(right, mask_r, __uint_as_float(r1[i])));   // 0/1 masks: zero padding outside the row
                         v[i] = fmaxf(fmaf(acc, a.inv_scale, s_bias[c0 + i]), 0.f);
                     }
 #pragma unroll
                     for (int g = 0; g < 2; g++) {
                         const size_t goff = (size_t)(c0 / 8 + g) * 1024 * 16;
-                        uint4 pk;
-                        pk.x = pack_h2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_h2(v[g * 8 + 2], v[g * 8 + 3]);
-                        pk.z = pack_h2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_h2(v[g * 8 + 6], v[g * 8 + 7]);
-                        *reinterpret_cast<uint4*>(obase + goff) = pk;
-                        if (OSA) {
-                            float l[8];
-#pragma unroll
-                            for (int e = 0; e < 8; e++) l[e] = v[g * 8 + e] - __half2float(__float2half_rn(v[g * 8 + e]));
-                            pk.x = pack_h2(l[0], l[1]); pk.y = pack_h2(l[2], l[3]); pk.z = pack_h2(l[4], l[5]); pk.w = pack_h2(l[6], l[7]);
-                            *reinterpret_cast<uint4*>(obase + (size_t)(COUT / 8) * 1024 * 16 + goff) = pk;
-                        }
+                        uint4 hi, lo;
+                        split_pack8<OSA>(v + g * 8, hi, lo);
+                        *reinterpret_cast<uint4*>(obase + goff) = hi;
+                        if (OSA) *reinterpret_cast<uint4*>(obase + (size_t)(COUT / 8) * 1024 * 16 + goff) = lo;
                     }
                 }
             }
@@ -322,16 +318,10 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
                     float v[8];
 #pragma unroll
                     for (int e = 0; e < 8; e++) v[e] = fmaxf(fmaf(__uint_as_float(r[g * 8 + e]), src.w1_inv, s_bias1[g * 8 + e]), 0.f);
-                    uint4 pk;
-                    pk.x = pack_h2(v[0], v[1]); pk.y = pack_h2(v[2], v[3]); pk.z = pack_h2(v[4], v[5]); pk.w = pack_h2(v[6], v[7]);
-                    *reinterpret_cast<uint4*>(st + ((size_t)g * GS + slot) * 16) = pk;
-                    if (SA) {
-                        float l[8];
-#pragma unroll
-                        for (int e = 0; e < 8; e++) l[e] = v[e] - __half2float(__float2half_rn(v[e]));
-                        pk.x = pack_h2(l[0], l[1]); pk.y = pack_h2(l[2], l[3]); pk.z = pack_h2(l[4], l[5]); pk.w = pack_h2(l[6], l[7]);
-                        *reinterpret_cast<uint4*>(st + ((size_t)(KC + g) * GS + slot) * 16) = pk;
-                    }
+                    uint4 hi, lo;
+                    split_pack8<SA>(v, hi, lo);
+                    *reinterpret_cast<uint4*>(st + ((size_t)g * GS + slot) * 16) = hi;
+                    if (SA) *reinterpret_cast<uint4*>(st + ((size_t)(KC + g) * GS + slot) * 16) = lo;
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -394,21 +384,43 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
             for (int k = 0; k < 4; k++) { const int p = pix_of(k); sx[((p >> 5) + 1) * 34 + (p & 31) + 1] = (v[k] - mean) * inv; }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             RP_WAIT(0, mbar_wait(p_empty, (it & 1) ^ 1));   // layer-1 MMAs of the previous patch have consumed the planes
+            // P planes, four slots (x = 4q .. 4q+3 of one row) per task: the 7 + 7 pixels they cover are split into fp16 hi / lo once and
+            // the four 16-byte windows are assembled with byte permutes
 #pragma unroll 1
-            for (int s0 = pt; s0 < NPIXP; s0 += 256) {
-                const int base = (s0 >> 5) * 34 + (s0 & 31);
-                float xv[8];
+            for (int task = pt; task < 34 * 8; task += 256) {
+                const int yy = task >> 3, xq = task & 7;
+                const float* rowp = sx + yy * 34 + 4 * xq;          // 8-byte aligned: 34 * 4 and 16 xq are multiples of 8
+                uint32_t H[2][4], Lo[2][4];                         // [row][pairs (0,1) (2,3) (4,5) (6,-)]
 #pragma unroll
-                for (int e = 0; e < 4; e++) { xv[e] = sx[base + e]; xv[4 + e] = sx[base + 34 + e]; }
-                uint4 hi;
-                hi.x = pack_h2(xv[0], xv[1]); hi.y = pack_h2(xv[2], xv[3]); hi.z = pack_h2(xv[4], xv[5]); hi.w = pack_h2(xv[6], xv[7]);
-                *reinterpret_cast<uint4*>(sP + (size_t)s0 * 16) = hi;
-                uint4 lo;
-                float r8[8];
+                for (int rr = 0; rr < 2; rr++) {
+                    const float2 p0 = *reinterpret_cast<const float2*>(rowp + rr * 34), p1 = *reinterpret_cast<const float2*>(rowp + rr * 34 + 2);
+                    const float2 p2 = *reinterpret_cast<const float2*>(rowp + rr * 34 + 4);
+                    const float p6 = rowp[rr * 34 + 6];
+                    const float xv[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p6, 0.f};
 #pragma unroll
-                for (int e = 0; e < 8; e++) r8[e] = xv[e] - __half2float(__float2half_rn(xv[e]));
-                lo.x = pack_h2(r8[0], r8[1]); lo.y = pack_h2(r8[2], r8[3]); lo.z = pack_h2(r8[4], r8[5]); lo.w = pack_h2(r8[6], r8[7]);
-                *reinterpret_cast<uint4*>(sP + (size_t)(NPIXP + s0) * 16) = lo;
+                    for (int i = 0; i < 4; i++) {
+                        const __half2 hh = __floats2half2_rn(xv[2 * i], xv[2 * i + 1]);
+                        const float2 f = __half22float2(hh);
+                        const __half2 ll = __floats2half2_rn(xv[2 * i] - f.x, xv[2 * i + 1] - f.y);
+                        H[rr][i] = *reinterpret_cast<const uint32_t*>(&hh);
+                        Lo[rr][i] = *reinterpret_cast<const uint32_t*>(&ll);
+                    }
+                }
+                auto window = [](const uint32_t (&P4)[4], int j, uint32_t& w0, uint32_t& w1) {   // elements j .. j+3 of the 7 as two half2
+                    if (j == 0) { w0 = P4[0]; w1 = P4[1]; }
+                    else if (j == 2) { w0 = P4[1]; w1 = P4[2]; }
+                    else if (j == 1) { w0 = __byte_perm(P4[0], P4[1], 0x5432); w1 = __byte_perm(P4[1], P4[2], 0x5432); }
+                    else { w0 = __byte_perm(P4[1], P4[2], 0x5432); w1 = __byte_perm(P4[2], P4[3], 0x5432); }
+                };
+                const int s0 = yy * 32 + 4 * xq;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint4 hi, lo;
+                    window(H[0], j, hi.x, hi.y); window(H[1], j, hi.z, hi.w);
+                    window(Lo[0], j, lo.x, lo.y); window(Lo[1], j, lo.z, lo.w);
+                    *reinterpret_cast<uint4*>(sP + (size_t)(s0 + j) * 16) = hi;
+                    *reinterpret_cast<uint4*>(sP + (size_t)(NPIXP + s0 + j) * 16) = lo;
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(p_full);

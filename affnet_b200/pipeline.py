@@ -12,14 +12,13 @@ class DetectDescribePipeline:
     def __init__(self, B, H, W, AffNet, HardNet, OriNet=None, num_features=2000, border=5, mrSize=5.192, nlevels=3,
                  init_sigma=1.6, do_ori=True, cand_cap=0, device="cuda"):
         self.cfg = L.PipelineConfig(B, H, W, num_features, nlevels, border, float(init_sigma), float(mrSize), 1 if do_ori else 0, cand_cap)
-        self.nets = (AffNet, OriNet, HardNet)  # keep the handles alive
-        h = C.c_void_p()
-        L.check(L.lib().ag_pipeline_create(C.byref(self.cfg), AffNet.handle(), OriNet.handle() if OriNet is not None else None,
-                                           HardNet.handle(), C.byref(h)))
-        self._h = h
+        self.nets = (AffNet, OriNet, HardNet)  # keep the modules alive; the C pipeline only BORROWS their ag_net_t handles
+        self._h = None
+        self._net_handles = None
+        self._bind_nets()
         self.B, self.H, self.W, self.K = B, H, W, num_features
         self.device = torch.device(device)
-        self.ws_bytes = L.lib().ag_pipeline_workspace_bytes(h)
+        self.ws_bytes = L.lib().ag_pipeline_workspace_bytes(self._h)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         self.lafs = torch.empty(B, num_features, 2, 3, dtype=torch.float32, device=self.device)
         self.resp = torch.empty(B, num_features, dtype=torch.float32, device=self.device)
@@ -27,6 +26,23 @@ class DetectDescribePipeline:
         self.count = torch.zeros(B, dtype=torch.int32, device=self.device)
         self._graph = None
         self._static_in = None
+
+    def _bind_nets(self):
+        """(Re)create the C pipeline over the nets' CURRENT handles.  A module rebuilds (and frees) its ag_net_t when its parameters
+        change (load_state_dict, .to(), in-place edits): the pipeline must never touch the freed handle, so every run()/replay() compares
+        the handle objects it was built with against the modules' and rebinds (run) or refuses (replay: the captured graph holds the
+        old weight pointers) when they differ."""
+        AffNet, OriNet, HardNet = self.nets
+        hs = (AffNet.handle(), OriNet.handle() if OriNet is not None else None, HardNet.handle())
+        if self._h is not None:
+            L.lib().ag_pipeline_destroy(self._h)
+            self._h = None
+        h = C.c_void_p()
+        L.check(L.lib().ag_pipeline_create(C.byref(self.cfg), hs[0], hs[1], hs[2], C.byref(h)))
+        self._h, self._net_handles, self._graph = h, hs, None
+
+    def _nets_current(self):
+        return all(n is None or n._handle is h for n, h in zip(self.nets, self._net_handles))
 
     def __del__(self):
         try:
@@ -42,6 +58,8 @@ class DetectDescribePipeline:
         """imgs CUDA float32 [B,1,H,W] or [B,H,W] -> (lafs [B,K,2,3] px, resp [B,K], desc [B,K,128], count [B]).
         Rows >= count[b] are unspecified.  No host synchronisation."""
         imgs = L.f32c(imgs, "imgs")
+        if not self._nets_current() or any(n is not None and n.handle() is not h for n, h in zip(self.nets, self._net_handles)):
+            self._bind_nets()      # a net was reloaded / moved since the pipeline was built
         if imgs.numel() != self.B * self.H * self.W:
             raise L.AffnetB200Error("expected %d x %d x %d pixels" % (self.B, self.H, self.W))
         L.check(L.lib().ag_pipeline_run(self._h, L.ptr(imgs), L.ptr(self.ws), self.ws_bytes, L.ptr(self.lafs), L.ptr(self.resp),
@@ -71,6 +89,8 @@ class DetectDescribePipeline:
     def replay(self, imgs=None):
         if self._graph is None:
             raise L.AffnetB200Error("call capture() first")
+        if not self._nets_current():
+            raise L.AffnetB200Error("a net of this pipeline was reloaded after capture(): the graph holds the old weights - call capture() again")
         if imgs is not None:
             self._static_in.copy_(imgs.view_as(self._static_in), non_blocking=True)
         self._graph.replay()

@@ -189,6 +189,17 @@ def make_ell():
     save("ell.npz", lafs=lafs, ell=ell, host_rows=np.nonzero(pos)[0], ell_host=ell_host)
 
 
+def make_jit():
+    """f4: the TorchScript exports of the reference (convertJIT/*.pt) run on CPU: raw head outputs on real and random patches."""
+    z = np.load(os.path.join(HERE, "graf_crop.npz"))
+    g = torch.Generator().manual_seed(17)
+    P = torch.cat([torch.from_numpy(z["aff_patches"])[:96], torch.rand(32, 1, 32, 32, generator=g) * 255.0]).float()
+    aff = torch.jit.load(os.path.join(R.REF, "convertJIT", "AffNetJIT.pt"), map_location="cpu").eval()
+    ori = torch.jit.load(os.path.join(R.REF, "convertJIT", "OriNetJIT.pt"), map_location="cpu").eval()
+    with torch.no_grad():
+        save("jit.npz", patches=P, affnet_raw=aff(P), orinet_raw=ori(P))
+
+
 def make_match():
     import importlib
     m = R.ref_modules()
@@ -220,7 +231,10 @@ if __name__ == "__main__":
         make_ell()
     elif len(sys.argv) > 1 and sys.argv[1] == "match":
         make_match()
+    elif len(sys.argv) > 1 and sys.argv[1] == "jit":
+        make_jit()
     else:
         main()
         make_ell()
         make_match()
+        make_jit()

@@ -108,3 +108,23 @@ def test_tcx_batching_invariance(L, nets):
         full = m(P)
         for lo, hi in ((0, 1), (1, 130), (130, 387), (386, 513), (512, 513), (3, 4)):
             assert torch.equal(m(P[lo:hi].contiguous()), full[lo:hi]), (type(m).__name__, lo, hi)
+
+
+def test_raw_heads_vs_reference_torchscript(L):
+    """f4 remainder: the raw head outputs (the contract of the reference's TorchScript exports) against goldens produced by running
+    convertJIT/AffNetJIT.pt and OriNetJIT.pt on CPU (tests/golden/make_golden.py::make_jit)."""
+    from affnet_b200.convertJIT import AffNetJIT, OriNetJIT
+    z = gold("jit.npz")
+    P = torch.from_numpy(z["patches"]).to(DEV)
+    a, o = AffNetJIT(), OriNetJIT()
+    a.load_state_dict(W["affnet"]); o.load_state_dict(W["orinet"])
+    a, o = a.eval().to(DEV), o.eval().to(DEV)
+    da = (a(P).cpu() - torch.from_numpy(z["affnet_raw"])).abs().max().item()
+    do = (o(P).cpu() - torch.from_numpy(z["orinet_raw"])).abs().max().item()
+    print("\nraw heads vs TorchScript goldens: AffNet %.2e, OriNet %.2e" % (da, do))
+    assert a(P).shape == (P.size(0), 3) and o(P).shape == (P.size(0), 2)
+    assert da < 2e-5 and do < 2e-5
+    for eng in (L.ENGINE_TC,):      # first-generation engine: same entry points
+        a.set_engine(eng); o.set_engine(eng)
+        assert (a(P).cpu() - torch.from_numpy(z["affnet_raw"])).abs().max() < 2e-5
+        assert (o(P).cpu() - torch.from_numpy(z["orinet_raw"])).abs().max() < 2e-5

@@ -135,3 +135,14 @@ def test_helpers_synthetic_image_is_the_oracles():
     import affnet_oracle as O
     from helpers import synthetic_image
     assert torch.equal(synthetic_image(96, 131, 7), O.synthetic_image(96, 131, 7))
+
+
+def test_orinet_signature_default_is_refused_at_construction():
+    """OriNetFast(PS=16) is the reference's signature default (architectures.py:33-35) but has neither checkpoint nor kernels: the
+    constructor refuses it (every caller of the reference passes PS=32), instead of failing at the first forward."""
+    import pytest as _pt
+    from affnet_b200 import _lib as L
+    from affnet_b200.architectures import OriNetFast
+    with _pt.raises(L.AffnetB200Error):
+        OriNetFast()
+    assert OriNetFast(PS=32).PS == 32

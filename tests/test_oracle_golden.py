@@ -195,3 +195,12 @@ def test_graf_1_to_6_application_counts(mode):
     tent, true = O.match_and_verify(L1, d1, L2, d2, torch.from_numpy(z["H1to6"]), float(z["snn"]), float(z["px"]))
     slack = 2 if mode == "hcori" else 0
     assert abs(tent - int(z[mode + "_tent"])) <= slack and abs(true - int(z[mode + "_true"])) <= slack, (tent, true)
+
+
+def test_raw_heads_match_the_reference_torchscript_exports():
+    """f4: convertJIT/AffNetJIT.pt returns xy + [1, 0, 1], OriNetJIT.pt the mean of tanh over the 3x3 map (golden: the .pt files run on CPU)."""
+    z = gold("jit.npz")
+    P = torch.from_numpy(z["patches"])
+    a = O.affnet_raw(P, W["affnet"]) + torch.tensor([[1.0, 0.0, 1.0]])
+    assert (a - torch.from_numpy(z["affnet_raw"])).abs().max() < 1e-5
+    assert (O.orinet_raw(P, W["orinet"]) - torch.from_numpy(z["orinet_raw"])).abs().max() < 1e-5
