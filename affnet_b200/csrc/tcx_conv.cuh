@@ -25,8 +25,9 @@
 //   L_S1_8P  stride-1 consumer on an 8x8 map    unit = PAIR    128 slots                    slot = (y*2 + p)*8 + x       (p = patch & 1)
 //   L_HEAD   the 8x8 head GEMM's A operand (tc_head.cuh): [patch/128][pixel*C/8 + c/8][patch%128][8] (+ a residual plane behind it)
 //
-// Warp roles: 0 loader (cp.async.bulk per channel group and plane) | 1 MMA issuer | 2.. epilogue (4 warps per set, EW/4 sets taking
-// tiles in turn: one tcgen05.ld stream reads 43 B/clk per warp, so wide accumulators want more readers).
+// Warp roles: 0 .. EW-1 epilogue (4 warps per set, EW/4 sets taking tiles in turn: one tcgen05.ld stream reads 43 B/clk per warp, so wide
+// accumulators want more readers) | EW loader (cp.async.bulk per channel group and plane) | EW+1 MMA issuer (the highest warp id: the SMSP
+// arbiter prefers it).
 #pragma once
 #include "tc_conv.cuh"
 
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
     }
     // zero rows of every stage: written once, the loader only ever writes data rows
     for (int i = threadIdx.x; i < (int)(Cfg::IN_BYTES / 16); i += blockDim.x) reinterpret_cast<uint4*>(sIn)[i] = make_uint4(0, 0, 0, 0);
-    if (warp == 1) {
+    if (warp == EW + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
     auto pvalid = [&](int pi) -> bool { return pi < a.n && (a.count == nullptr || (pi % a.group) < a.count[pi / a.group]); };
     auto uvalid = [&](int u) -> bool { return PAIR ? (pvalid(2 * u) || pvalid(2 * u + 1)) : pvalid(u); };
 
-    if (warp == 0) {
+    if (warp == EW) {
         // ===== loader =====
         if (lane == 0) {
             mbar_expect_tx(wbar, Cfg::W_BYTES);
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
             }
             XP_STORE(a.prof_id, 3);
         }
-    } else if (warp == 1) {
+    } else if (warp == EW + 1) {
         // ===== MMA issuer (warp-uniform control flow, one elected lane issues) =====
         constexpr uint32_t idesc3 = (1u << 4) | ((uint32_t)((3 * NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
         // ===== epilogue: EW / 4 sets of four warps (TMEM lane quadrant = warp % 4), set k takes tiles k, k + NSETS, ... =====
         constexpr int NSETS = EW / 4;
         const int q = warp & 3;
-        const int set = (warp - 2) >> 2;
+        const int set = warp >> 2;
         const int r = q * 32 + lane;                         // tile row of this thread
         int tcnt = 0;
         RP_DECL;
@@ -353,11 +354,11 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
                 }
             }
         }
-        if (warp == 2) XP_STORE(a.prof_id, 1);
+        if (warp == 0) XP_STORE(a.prof_id, 1);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == EW + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }

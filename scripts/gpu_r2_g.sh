@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_tcx.py -q -s > gpurun_out/pytest_tcx.log 2>&1; echo "pytest rc=$?"
-grep -E "engine|passed|failed|FAILED" gpurun_out/pytest_tcx.log | head
+timeout 600 python -m pytest tests/test_gpu_tcx.py tests/test_gpu_parity.py -q -s > gpurun_out/pytest_tcx.log 2>&1; echo "pytest rc=$?"
+grep -E "engine|passed|failed|FAILED|raw heads|Error" gpurun_out/pytest_tcx.log | head -20
 AFFNET_B200_LIB=$PWD/affnet_b200/lib/libaffnet_b200_xprof.so timeout 300 python scripts/role_prof_x.py 48000 2>&1 | tee gpurun_out/role_prof_x.txt | grep -A5 "slot 0\|==" | head -60
 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_tc2.json 2> gpurun_out/bench_tc2.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_tc2.err
 python - <<'PY'
