@@ -10,6 +10,8 @@
 
 #include <vector>
 
+#include <cuda_bf16.h>
+
 #include "net_impl.cuh"
 
 namespace ag {
@@ -412,6 +414,26 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
         tcx_pack_layer(packed.data() + w_off[l], cfg[l].cin, cfg[l].cout, tcx_stride(l), tcx_nsplit(kind, l), tcx_split_w(kind, l), w_scale[l], packed_x);
         while (packed_x.size() % 8) packed_x.push_back(__float2half_rn(0.f));
     }
+    // HardNet: the same packs with bf16 operands (engine 5, BASELINE.json configs[4]) + the bf16 head weights
+    std::vector<__half> packed_bf;
+    size_t wbf_off[6] = {0, 0, 0, 0, 0, 0}, headbf_off = 0;
+    if (kind == AG_NET_HARDNET) {
+        for (int l = 1; l < 6; l++) {
+            wbf_off[l] = packed_bf.size();
+            tcx_pack_layer(packed.data() + w_off[l], cfg[l].cin, cfg[l].cout, tcx_stride(l), tcx_nsplit(kind, l), tcx_split_w(kind, l), w_scale[l], packed_bf, 1);
+            while (packed_bf.size() % 8) packed_bf.push_back(__float2half_rn(0.f));
+        }
+        headbf_off = packed_bf.size();
+        packed_bf.resize(packed_bf.size() + (size_t)8192 * 128);
+        const float* hw = packed.data() + hw_off;  // [k = c*64 + p][cout]
+        for (int pix = 0; pix < 64; pix++)
+            for (int cg = 0; cg < 16; cg++)
+                for (int o = 0; o < 128; o++)
+                    for (int e = 0; e < 8; e++) {
+                        const __nv_bfloat16 bv = __float2bfloat16_rn(hw[((size_t)(cg * 8 + e) * 64 + pix) * 128 + o]);
+                        memcpy(&packed_bf[headbf_off + (((size_t)(pix * 16 + cg)) * 128 + o) * 8 + e], &bv, 2);
+                    }
+    }
     size_t headh_off = 0;
     float head_scale = 1.0f;
     if (kind == AG_NET_HARDNET) {
@@ -465,6 +487,15 @@ int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out
         if (rch == AG_OK) rch = check_cuda(cudaMemcpy(net->d_all_x, packed_x.data(), packed_x.size() * sizeof(__half), cudaMemcpyHostToDevice), "upload fp16 weights");
         if (rch != AG_OK) { cudaFree(net->d_all_h); cudaFree(net->d_all_x); delete net; return rch; }
         for (int l = 1; l < 6; l++) net->d_wx[l] = net->d_all_x + wx_off[l];
+        if (!packed_bf.empty()) {   // appended behind the fp16 packs in a second allocation owned through d_wx_bf[0]
+            __half* dbf = nullptr;
+            rch = check_cuda(cudaMalloc(&dbf, packed_bf.size() * sizeof(__half)), "cudaMalloc bf16 weights");
+            if (rch == AG_OK) rch = check_cuda(cudaMemcpy(dbf, packed_bf.data(), packed_bf.size() * sizeof(__half), cudaMemcpyHostToDevice), "upload bf16 weights");
+            if (rch != AG_OK) { cudaFree(dbf); cudaFree(net->d_all_h); cudaFree(net->d_all_x); delete net; return rch; }
+            net->d_wx_bf[0] = dbf;
+            for (int l = 1; l < 6; l++) net->d_wx_bf[l] = dbf + wbf_off[l];
+            net->d_headh_bf = dbf + headbf_off;
+        }
     }
     int rc = check_cuda(cudaMalloc(&net->d_all, packed.size() * sizeof(float)), "cudaMalloc weights");
     if (rc != AG_OK) { cudaFree(net->d_all_h); cudaFree(net->d_all_x); delete net; return rc; }
@@ -483,12 +514,14 @@ void ag_net_destroy(ag_net_t* net) {
     cudaFree(net->d_all);
     cudaFree(net->d_all_h);
     cudaFree(net->d_all_x);
+    cudaFree(net->d_wx_bf[0]);
     delete net;
 }
 
 int ag_net_set_engine(ag_net_t* net, int engine) {
     AG_REQUIRE(net != nullptr, "NULL net");
-    AG_REQUIRE(engine == AG_ENGINE_SIMT || engine == AG_ENGINE_TC || engine == AG_ENGINE_TC_EXACT || engine == AG_ENGINE_TC_FAST || engine == AG_ENGINE_TC2, "unknown engine");
+    AG_REQUIRE(engine == AG_ENGINE_SIMT || engine == AG_ENGINE_TC || engine == AG_ENGINE_TC_EXACT || engine == AG_ENGINE_TC_FAST || engine == AG_ENGINE_TC2 || engine == AG_ENGINE_TC2_BF16, "unknown engine");
+    AG_REQUIRE(engine != AG_ENGINE_TC2_BF16 || net->kind == AG_NET_HARDNET, "the bf16 engine exists for HardNet only");
     AG_REQUIRE(engine != AG_ENGINE_TC_FAST || net->kind == AG_NET_AFFNET, "the fast tensor-core engine exists for AffNet only");
     AG_REQUIRE(engine != AG_ENGINE_TC_EXACT || net->kind != AG_NET_HARDNET, "the exact tensor-core engine exists for AffNet / OriNet");
     net->engine = engine;
@@ -626,12 +659,13 @@ static int hardnet_impl(const ag_net_t* net, const float* d_patches, const tc::F
     int rc = split_ws(net->kind, n, d_ws, ws_bytes, &a, &b);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (net->engine == AG_ENGINE_TC2) {
+    if (net->engine == AG_ENGINE_TC2 || net->engine == AG_ENGINE_TC2_BF16) {
+        const int bf = net->engine == AG_ENGINE_TC2_BF16;
         char* base = (char*)d_ws;
         const size_t act = align_up(tcx_act_bytes(n), 256);
         const tc::FirstSrc s0 = src ? *src : tc_src_patches(d_patches);
-        if ((rc = tcx_trunk_hardnet(net, s0, n, group, d_count, base, base + act, base + 2 * act, st, 6))) return rc;
-        return tc_hardnet_head(net, base + 2 * act, n, group, d_count, d_out, st);
+        if ((rc = tcx_trunk_hardnet(net, s0, n, group, d_count, base, base + act, base + 2 * act, st, 6, bf))) return rc;
+        return tc_hardnet_head(net, base + 2 * act, n, group, d_count, d_out, st, bf);
     }
     if (net->engine == AG_ENGINE_TC) {
         char* base = (char*)d_ws;

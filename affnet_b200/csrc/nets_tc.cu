@@ -160,15 +160,17 @@ int tc_hardnet_forward(const ag_net* net, const tc::FirstSrc& src0, int n, int g
 }
 
 // HardNet 8x8 head GEMM + BatchNorm + L2 norm over the head operand a trunk left in `headbuf`
-int tc_hardnet_head(const ag_net* net, const void* headbuf, int n, int group, const int* count, float* out, cudaStream_t st) {
+int tc_hardnet_head(const ag_net* net, const void* headbuf, int n, int group, const int* count, float* out, cudaStream_t st, int bf16) {
     using namespace tc;
     static bool configured = false;
     if (!configured) {
-        int rc = check_cuda(cudaFuncSetAttribute(tc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM), "tc_head smem attr");
+        int rc = check_cuda(cudaFuncSetAttribute(tc_head_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM), "tc_head smem attr");
+        if (rc == AG_OK) rc = check_cuda(cudaFuncSetAttribute(tc_head_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM), "tc_head smem attr");
         if (rc != AG_OK) return rc;
         configured = true;
     }
-    tc_head_kernel<<<(n + 127) / 128, 192, HEAD_SMEM, st>>>((const __half*)headbuf, net->d_headh, net->d_head_b, out, n, group, count);
+    if (bf16) tc_head_kernel<1><<<(n + 127) / 128, 192, HEAD_SMEM, st>>>((const __half*)headbuf, net->d_headh_bf, net->d_head_b, out, n, group, count);
+    else tc_head_kernel<0><<<(n + 127) / 128, 192, HEAD_SMEM, st>>>((const __half*)headbuf, net->d_headh, net->d_head_b, out, n, group, count);
     AG_CHECK_LAUNCH("tc_head_kernel");
     return AG_OK;
 }

@@ -10,6 +10,8 @@
 
 #include <vector>
 
+#include <cuda_bf16.h>
+
 #include "net_impl.cuh"
 #include "tcx_conv.cuh"
 #include "tcx_first.cuh"
@@ -38,11 +40,11 @@ static int ensure_smem_attr(const void* func, int bytes, bool* configured, const
     return rc;
 }
 
-template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW>
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW, int BF = 0>
 static int launch_conv(const void* in, void* out, const __half* w, const float* b, float inv_scale, int n, int group, const int* count, cudaStream_t st) {
     constexpr int prof_id = (H == 32) ? 2 : (H == 16 ? (STRIDE == 1 ? 3 : 4) : 5);
     using Cfg = XCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW>;
-    auto kern = tcx_conv_kernel<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW>;
+    auto kern = tcx_conv_kernel<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW, BF>;
     static bool configured[64] = {};   // per device (the attribute is per device)
     int rc = ensure_smem_attr((const void*)kern, (int)Cfg::SMEM, configured, "tcx_conv smem attr");
     if (rc != AG_OK) return rc;
@@ -57,10 +59,10 @@ static int launch_conv(const void* in, void* out, const __half* w, const float* 
     return AG_OK;
 }
 
-template <int C1, int COUT, int SA, int SW, int OSA>
+template <int C1, int COUT, int SA, int SW, int OSA, int BF = 0>
 static int launch_first(void* out, const __half* w, const float* b, float inv_scale, int n, int group, const int* count, cudaStream_t st, const FirstSrc& src) {
     using Cfg = XFirstCfg<C1, COUT, SA, SW, OSA>;
-    auto kern = tcx_first_kernel<C1, COUT, SA, SW, OSA>;
+    auto kern = tcx_first_kernel<C1, COUT, SA, SW, OSA, BF>;
     static bool configured[64] = {};
     int rc = ensure_smem_attr((const void*)kern, (int)Cfg::SMEM, configured, "tcx_first smem attr");
     if (rc != AG_OK) return rc;
@@ -95,12 +97,25 @@ __global__ void tcx_decode_kernel(const __half* __restrict__ buf, int layout, in
 // wf: fp32 [tap = dy*3+dx][ci][co] (BatchNorm folded), scale: power of two.  Blocks per (split, dy, 16 input channels):
 //   stride 1: [K group (2)][part hi|lo][dx 0,1,2][co][8]
 //   stride 2: odd-x plane [K group][part][dx 0,2][co][8], then even-x plane [K group][part][dx 1][co][8]
-void tcx_pack_layer(const float* wf, int ci, int co, int stride, int nsplit, int sw, float scale, std::vector<__half>& out) {
+static __half bf16_bits_as_half(float v) {   // bf16(v) stored in a 16-bit slot of the (type-agnostic) weight buffer
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    __half h;
+    memcpy(&h, &b, 2);
+    return h;
+}
+static float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+void tcx_pack_layer(const float* wf, int ci, int co, int stride, int nsplit, int sw, float scale, std::vector<__half>& out, int bf16) {
     const int nt = co / nsplit;
     auto put = [&](int dy, int dx, int cin, int c, int part) {
         const float v = scale * wf[((size_t)(dy * 3 + dx) * ci + cin) * co + c];
-        const __half hi = __float2half_rn(v);
-        out.push_back(part == 0 ? hi : __float2half_rn(v - __half2float(hi)));
+        if (bf16) {
+            const float hi = bf16_round(v);
+            out.push_back(bf16_bits_as_half(part == 0 ? hi : v - hi));
+        } else {
+            const __half hi = __float2half_rn(v);
+            out.push_back(part == 0 ? hi : __float2half_rn(v - __half2float(hi)));
+        }
     };
     for (int sp = 0; sp < nsplit; sp++)
         for (int dy = 0; dy < 3; dy++)
@@ -153,21 +168,29 @@ int tcx_trunk_affori(const ag_net* net, const tc::FirstSrc& src0, int n, int gro
     return launch_conv<64, 64, 8, 1, 1, 2, L_HEAD, 1, 1, 1, 8>(bufA, feat, net->d_wx[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st);
 }
 
-int tcx_trunk_hardnet(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, void* headbuf,
-                      cudaStream_t st, int upto) {
+template <int BF>
+static int trunk_hardnet_t(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, void* headbuf,
+                           cudaStream_t st, int upto) {
     using namespace tcx;
     tc::FirstSrc src = src0;
     src.w1 = net->d_w1; src.b1 = net->d_b[0]; src.w1_inv = net->w_inv_scale[0]; src.w1_scale = 1.0f / net->w_inv_scale[0];
+    __half* const* wx = BF ? net->d_wx_bf : net->d_wx;
     int rc;
-    if ((rc = launch_first<32, 32, 0, 1, 0>(bufB, net->d_wx[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src))) return rc;
+    if ((rc = launch_first<32, 32, 0, 1, 0, BF>(bufB, wx[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src))) return rc;
     if (upto <= 2) return AG_OK;
-    if ((rc = launch_conv<32, 64, 32, 2, 1, 2, L_S1_16, 0, 1, 0, 8>(bufB, bufA, net->d_wx[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
+    if ((rc = launch_conv<32, 64, 32, 2, 1, 2, L_S1_16, 0, 1, 0, 8, BF>(bufB, bufA, wx[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
     if (upto <= 3) return AG_OK;
-    if ((rc = launch_conv<64, 64, 16, 1, 1, 2, L_S2_8P, 0, 1, 0, 8>(bufA, bufB, net->d_wx[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
+    if ((rc = launch_conv<64, 64, 16, 1, 1, 2, L_S2_8P, 0, 1, 0, 8, BF>(bufA, bufB, wx[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
     if (upto <= 4) return AG_OK;
-    if ((rc = launch_conv<64, 128, 16, 2, 2, 2, L_S1_8P, 0, 0, 0, 8>(bufB, bufA, net->d_wx[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
+    if ((rc = launch_conv<64, 128, 16, 2, 2, 2, L_S1_8P, 0, 0, 0, 8, BF>(bufB, bufA, wx[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
     if (upto <= 5) return AG_OK;
-    return launch_conv<128, 128, 8, 1, 2, 2, L_HEAD, 0, 0, 0, 8>(bufA, headbuf, net->d_wx[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st);
+    return launch_conv<128, 128, 8, 1, 2, 2, L_HEAD, 0, 0, 0, 8, BF>(bufA, headbuf, wx[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st);
+}
+
+int tcx_trunk_hardnet(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, void* headbuf,
+                      cudaStream_t st, int upto, int bf16) {
+    return bf16 ? trunk_hardnet_t<1>(net, src0, n, group, count, bufA, bufB, headbuf, st, upto)
+                : trunk_hardnet_t<0>(net, src0, n, group, count, bufA, bufB, headbuf, st, upto);
 }
 
 }  // namespace ag

@@ -13,6 +13,7 @@ constexpr int HEAD_K = 8192, HEAD_N = 128, HEAD_KS = 64, HEAD_STAGES = 6;
 constexpr uint32_t HEAD_STAGE_A = (HEAD_KS / 8) * 128 * 16, HEAD_STAGE_B = (HEAD_KS / 8) * HEAD_N * 16;
 constexpr size_t HEAD_SMEM = 1024 + (size_t)HEAD_STAGES * (HEAD_STAGE_A + HEAD_STAGE_B);
 
+template <int BF>
 __global__ void __launch_bounds__(192, 1) tc_head_kernel(const __half* __restrict__ feat, const __half* __restrict__ wh,
                                                           const float* __restrict__ bn /*scale[128], shift[128]*/, float* __restrict__ out,
                                                           int n, int group, const int* __restrict__ count) {
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(192, 1) tc_head_kernel(const __half* __restric
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(HEAD_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t idesc = (BF ? ((1u << 7) | (1u << 10)) : 0u) | (1u << 4) | ((uint32_t)(HEAD_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // BF: bf16 operands
             for (int k = 0; k < NK; k++) {
                 const int s = k % HEAD_STAGES;
                 mbar_wait(&full[s], (k / HEAD_STAGES) & 1);

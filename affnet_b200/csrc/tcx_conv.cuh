@@ -29,6 +29,8 @@
 // accumulators want more readers) | EW loader (cp.async.bulk per channel group and plane) | EW+1 MMA issuer (the highest warp id: the SMSP
 // arbiter prefers it).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "tc_conv.cuh"
 
 namespace ag {
@@ -53,18 +55,31 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "r"(taddr));
 }
 
-// 8 fp32 values -> 8 fp16 (hi) and, when LO, the fp16 residuals v - fp16(v); the residual is taken from the packed hi (one F2FP per pair)
-template <int LO>
+// Operand type of an engine instance: BF = 0 fp16, BF = 1 bf16 (BASELINE.json configs[4]: "bf16 HardNet tensor-core path"); the MMA kind
+// is kind::f16 for both, the instruction descriptor carries the A / B formats.
+template <int BF> struct XFmt { static constexpr uint32_t IDESC = BF ? ((1u << 7) | (1u << 10)) : 0u; };
+template <int BF>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    if (BF) { const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <int BF>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+    if (BF) return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+// 8 fp32 values -> 8 16-bit floats (hi) and, when LO, the residuals v - hi rounded to the same format; the residual is taken from the
+// packed hi (one F2FP per pair)
+template <int LO, int BF = 0>
 __device__ __forceinline__ void split_pack8(const float* v, uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        h[i] = pack2<BF>(v[2 * i], v[2 * i + 1]);
         if (LO) {
-            const float2 f = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
-            l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+            const float2 f = unpack2<BF>(h[i]);
+            l[i] = pack2<BF>(v[2 * i] - f.x, v[2 * i + 1] - f.y);
         } else l[i] = 0;
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
@@ -137,7 +152,7 @@ struct XCfg {
     static_assert(OUT == L_HEAD || layout_pair(OUT) || !In::PAIR, "a pair layer writes pair layouts or the head operand");
 };
 
-template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW>
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW, int BF = 0>
 __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a) {
     using Cfg = XCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW>;
     using In = typename Cfg::In;
@@ -205,9 +220,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
         }
     } else if (warp == EW + 1) {
         // ===== MMA issuer (warp-uniform control flow, one elected lane issues) =====
-        constexpr uint32_t idesc3 = (1u << 4) | ((uint32_t)((3 * NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc3 = XFmt<BF>::IDESC | (1u << 4) | ((uint32_t)((3 * NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc2 = XFmt<BF>::IDESC | (1u << 4) | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc1 = XFmt<BF>::IDESC | (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t leader = elect_one();
         mbar_wait(wbar, 0);
         tc_fence_after();
@@ -346,7 +361,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
                             const int cg = (split * NT + c0) / 8 + g;       // channel group of the output
                             const size_t goff = (OUT == L_HEAD) ? (size_t)cg * 128 * 16 : (size_t)cg * layout_slots(OUT) * 16;
                             uint4 hi, lo;
-                            split_pack8<OSA>(v + g * 8, hi, lo);
+                            split_pack8<OSA, BF>(v + g * 8, hi, lo);
                             *reinterpret_cast<uint4*>(obase + goff) = hi;
                             if (OSA) *reinterpret_cast<uint4*>(obase + lo_off + goff) = lo;
                         }

@@ -53,7 +53,7 @@ struct XFirstCfg {
     static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-template <int C1, int COUT, int SA, int SW, int OSA>
+template <int C1, int COUT, int SA, int SW, int OSA, int BF = 0>
 __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, const FirstSrc src) {
     using Cfg = XFirstCfg<C1, COUT, SA, SW, OSA>;
     constexpr int KC = Cfg::KC, NT = Cfg::NT, NACC = Cfg::NACC, TILES = Cfg::TILES, NPIXP = Cfg::NPIXP, SX = Cfg::SX, GS = Cfg::GS, NL1 = Cfg::NL1;
@@ -100,10 +100,10 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
         float v = 0.f;
         if (dx < 3 && (ch == 0 || e < 4)) {
             const float wv = src.w1[(dy * 3 + dx) * C1 + co] * src.w1_scale;   // power-of-two scale, undone in the epilogue
-            const __half hi = __float2half_rn(wv);
-            v = part == 0 ? __half2float(hi) : wv - __half2float(hi);
+            const float hi = unpack2<BF>(pack2<BF>(wv, 0.f)).x;      // wv rounded to the operand format
+            v = part == 0 ? hi : wv - hi;
         }
-        reinterpret_cast<__half*>(sW1)[i] = __float2half_rn(v);
+        reinterpret_cast<unsigned short*>(sW1)[i] = (unsigned short)(pack2<BF>(v, 0.f) & 0xFFFFu);
     }
     for (int i = threadIdx.x; i < (int)((Cfg::IN_BYTES + Cfg::P_BYTES) / 16); i += blockDim.x) reinterpret_cast<uint4*>(sIn)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < 2 * SX; i += blockDim.x) s_x[i] = 0.f;
@@ -120,10 +120,10 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
 
     if (warp == 20) {
         // ===== MMA issuer: layer 1 runs one patch ahead of layer 2 =====
-        constexpr uint32_t idesc_all = (1u << 4) | ((uint32_t)(Cfg::ACCW >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);      // N = 3 NT (or 6 NT stacked)
-        constexpr uint32_t idesc_3 = (1u << 4) | ((uint32_t)((3 * NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(C1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t idesc1_st = (1u << 4) | ((uint32_t)((2 * C1) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc_all = XFmt<BF>::IDESC | (1u << 4) | ((uint32_t)(Cfg::ACCW >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);      // N = 3 NT (or 6 NT stacked)
+        constexpr uint32_t idesc_3 = XFmt<BF>::IDESC | (1u << 4) | ((uint32_t)((3 * NT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc1 = XFmt<BF>::IDESC | (1u << 4) | ((uint32_t)(C1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc1_st = XFmt<BF>::IDESC | (1u << 4) | ((uint32_t)((2 * C1) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t leader = elect_one();
         if (leader) {
             mbar_expect_tx(wbar, Cfg::W_BYTES);
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
                     for (int g = 0; g < 2; g++) {
                         const size_t goff = (size_t)(c0 / 8 + g) * 1024 * 16;
                         uint4 hi, lo;
-                        split_pack8<OSA>(v + g * 8, hi, lo);
+                        split_pack8<OSA, BF>(v + g * 8, hi, lo);
                         *reinterpret_cast<uint4*>(obase + goff) = hi;
                         if (OSA) *reinterpret_cast<uint4*>(obase + (size_t)(COUT / 8) * 1024 * 16 + goff) = lo;
                     }
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
 #pragma unroll
                     for (int e = 0; e < 8; e++) v[e] = fmaxf(fmaf(__uint_as_float(r[g * 8 + e]), src.w1_inv, bias1[g * 8 + e]), 0.f);
                     uint4 hi, lo;
-                    split_pack8<SA>(v, hi, lo);
+                    split_pack8<SA, BF>(v, hi, lo);
                     *reinterpret_cast<uint4*>(st + ((size_t)g * GS + slot) * 16) = hi;
                     if (SA) *reinterpret_cast<uint4*>(st + ((size_t)(KC + g) * GS + slot) * 16) = lo;
                 }
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(21 * 32, 1) tcx_first_kernel(const XArgs a, co
 #pragma unroll
                     for (int e = 0; e < 4; e++) { xv[e] = rowp[e]; xv[4 + e] = rowp[34 + e]; }
                     uint4 hi, lo;
-                    split_pack8<1>(xv, hi, lo);
+                    split_pack8<1, BF>(xv, hi, lo);
                     *reinterpret_cast<uint4*>(ph + (size_t)s0 * 16) = hi;
                     *reinterpret_cast<uint4*>(ph + (size_t)(NPIXP + s0) * 16) = lo;
                 }

@@ -429,6 +429,8 @@ def _main(real_stdout):
     a, o, h = a.eval().to(dev), o.eval().to(dev), h.eval().to(dev)
     H, W, K, border, B0, label = CONFIGS[args.config]
     B = args.batch or B0
+    if args.config == "5":      # BASELINE.json configs[4]: "bf16 HardNet tensor-core path"
+        h.set_engine(L.ENGINE_TC2_BF16)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()   # nvidia-smi needs a few hundred ms to deliver its first sample: start it long before the timed region
@@ -492,9 +494,11 @@ def _main(real_stdout):
         for name, cfg, b, st in plan:
             try:
                 Hh, Ww, Kk, bb, _, lab = CONFIGS[cfg]
+                h.set_engine(L.ENGINE_TC2_BF16 if cfg == "5" else L.ENGINE_TC2)     # configs[4] names the bf16 HardNet path
                 w2 = Workload(ctx, Hh, Ww, Kk, bb, b, use_graph)
                 extra[name] = w2.summary(st, 3, e2e=True)
                 extra[name]["config"] = lab
+                extra[name]["hardnet_operands"] = "bf16" if cfg == "5" else "fp16"
                 w2.close()
             except Exception as e:   # noqa: BLE001  (an extra must never cost the headline line)
                 extra[name] = {"error": str(e)[:300]}
@@ -516,7 +520,8 @@ def _main(real_stdout):
         e2e_v = pix / (e2e_ms / args.steps * 1e-3) / 1e6
         line = {"metric": "Mpix/s end-to-end HesAffNet(+OriNet)+HardNet", "value": value, "unit": "Mpix/s",
                 "kpatches_per_s": world * n_desc / (ms_per_step * 1e-3) / 1e3, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": DTYPE.replace("fp16 operands", "fp16 operands (HardNet: bf16 operands, configs[4])") if args.config == "5" else DTYPE,
                 "data": "synthetic images (seeded noise, blur sigma 2, stretched), pretrained weights from tests/golden",
                 "config": {"workload": "%dx%d grayscale, %d kpts/img, batch of %d images per GPU per step (%s)" % (W, H, K, B, label),
                            "do_ori": True, "border": border, "mrSize": 5.192, "cuda_graph": use_graph, "l2": "256 MiB flush write between timed steps (device-resident leg); e2e leg: fresh inputs arrive by DMA every step, no flush",

@@ -409,6 +409,17 @@ def test_benchmark_configs_vs_oracle(L, nets, cfg):
     rep = parity_report(oL, odesc, lafs[0, :n].cpu(), desc[0, :n].cpu(), "%s K=%d border=%d vs oracle" % (cfg, K, border))
     assert abs(n - oL.shape[0]) <= 0.005 * K and rep["matched"] >= 0.995 * oL.shape[0], rep
     assert rep["eA"] < TOL and rep["ec"] < TOL and rep["dd"] < TOL, rep
+    if cfg == "4k":      # BASELINE.json configs[4] names a bf16 HardNet path: same keypoints, descriptors at bf16's own tolerance
+        try:
+            lafs_ref, cnt_ref = lafs.clone(), cnt.clone()       # run() returns the pipeline's own (reused) buffers
+            hn.set_engine(L.ENGINE_TC2_BF16)
+            l2, r2, d2, c2 = pipe.run(img.to(DEV))
+            torch.cuda.synchronize()
+            assert torch.equal(c2, cnt_ref) and torch.equal(l2[0, :n], lafs_ref[0, :n])
+            rb = parity_report(oL, odesc, l2[0, :n].cpu(), d2[0, :n].cpu(), "4k, HardNet bf16 operands, vs oracle")
+            assert rb["dd"] < 1e-2, rb
+        finally:
+            hn.set_engine(L.ENGINE_TC2)
 
 
 def test_handcrafted_estimators_8f(L):
