@@ -733,22 +733,46 @@ struct SelectParams {
     int* count;
 };
 
+// A cluster of SEL_CL CTAs per image (thread-block cluster, distributed shared memory): every CTA scans 1/SEL_CL of the candidate list,
+// the per-pass histograms of the radix select are merged by CTA 0 through DSMEM, the selected candidates are appended to CTA 0's sort
+// buffer with DSMEM atomics, and CTA 0 sorts and writes the output.  The radix select stops as soon as the chosen digit's bucket is needed
+// entirely (typically after 2-3 of the 8 passes).  (r01: one CTA per image, 8 full passes, serial histogram scan: 0.18 ms for 16 images,
+// 0.88 ms for one 4K image.)
+constexpr int SEL_CL = 8;
+
+__device__ __forceinline__ uint32_t dsmem_addr(const void* p, int rank) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ int dsmem_ld_i32(uint32_t a) { int v; asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long dsmem_ld_u64(uint32_t a) { unsigned long long v; asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void dsmem_st_i32(uint32_t a, int v) { asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void dsmem_st_u64(uint32_t a, unsigned long long v) { asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ int dsmem_atomic_add(uint32_t a, int v) { int o; asm volatile("atom.shared::cluster.add.s32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(SNT) select_kernel(const SelectParams P) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);                                    // used by cluster rank 0
     int* s_idx = reinterpret_cast<int*>(smem_raw + sizeof(unsigned long long) * P.sort_cap);
     __shared__ int s_hist[256];
     __shared__ unsigned s_accept;  // bit per slot
-    __shared__ int s_misc[4];      // 0: sorted mode, 1: m (number to select), 2: digit, 3: fill counter
-    __shared__ unsigned long long s_prefix;
+    __shared__ int s_misc[4];      // 0: sorted mode, 1: m (number to select), 2: still needed inside the chosen digit / done flag (rank 0), 3: fill counter (rank 0)
+    __shared__ unsigned long long s_prefix;   // rank 0 publishes the radix prefix here
+    __shared__ int s_ctl[2];       // rank 0: [0] remaining, [1] done
 
-    const int b = blockIdx.x;
+    unsigned rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int b = blockIdx.x / SEL_CL;
     const int n = min(P.cand_count[b], P.cand_cap);
     const float* val = P.cand_val + (size_t)b * P.cand_cap;
     const uint32_t* seq = P.cand_seq + (size_t)b * P.cand_cap;
     const int nf = P.num_features;
 
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {   // every CTA of the cluster derives the same selection parameters
         unsigned acc = 0;
         long long total = 0;
         bool trimmed = false;
@@ -769,6 +793,7 @@ __global__ void __launch_bounds__(SNT) select_kernel(const SelectParams P) {
         s_misc[1] = (int)m;
         s_misc[3] = 0;
         s_prefix = 0ull;
+        s_ctl[0] = (int)m; s_ctl[1] = 0;
     }
     __syncthreads();
     const unsigned accept = s_accept;
@@ -782,45 +807,80 @@ __global__ void __launch_bounds__(SNT) select_kernel(const SelectParams P) {
         // +1 keeps every valid key above the invalid key 0
         return sorted ? (((unsigned long long)float_to_ordered(val[i]) << 32) | lo) : (lo + 1ull);
     };
+    const uint32_t r0_prefix = dsmem_addr(&s_prefix, 0), r0_ctl = dsmem_addr(s_ctl, 0);
+    const uint32_t r0_fill = dsmem_addr(&s_misc[3], 0), r0_key = dsmem_addr(s_key, 0), r0_idx = dsmem_addr(s_idx, 0);
 
-    if (m > 0) {
-        // radix select of the m-th largest key, 8 bits per pass from the top
-        int remaining = m;
+    unsigned long long kth = 1ull;   // unsorted mode: every valid key (>= 1) is taken
+    if (m > 0 && sorted) {
+        // radix select of the m-th largest key, 8 bits per pass from the top; candidates are dealt round-robin to the CTAs of the cluster
+        unsigned long long prefix = 0ull;
         for (int pass = 7; pass >= 0; pass--) {
             for (int i = threadIdx.x; i < 256; i += SNT) s_hist[i] = 0;
             __syncthreads();
-            const unsigned long long prefix = s_prefix;
             const int shift = pass * 8;
             const unsigned long long hi_mask = (pass == 7) ? 0ull : (~0ull << (shift + 8));
-            for (int i = threadIdx.x; i < n; i += SNT) {
+            for (int i = (int)rank * SNT + threadIdx.x; i < n; i += SEL_CL * SNT) {
                 const unsigned long long k = key_of(i);
                 if ((k & hi_mask) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & 0xFF)], 1);
             }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int cum = 0, d = 255;
-                for (; d > 0; d--) {
-                    if (cum + s_hist[d] >= remaining) break;
-                    cum += s_hist[d];
+            cluster_sync_all();                      // all local histograms complete
+            if (rank == 0) {
+                if (threadIdx.x < 256) {             // merge the other CTAs' histograms into this one
+                    int t = s_hist[threadIdx.x];
+                    for (int r = 1; r < SEL_CL; r++) t += dsmem_ld_i32(dsmem_addr(&s_hist[threadIdx.x], r));
+                    s_hist[threadIdx.x] = t;
                 }
-                s_misc[2] = remaining - cum;  // still needed inside digit d
-                s_prefix = prefix | ((unsigned long long)d << shift);
+                __syncthreads();
+                if (threadIdx.x < 32) {              // warp 0: suffix sums over the 256 bins, 8 bins per lane (lane 31 = top digits)
+                    const int lane = threadIdx.x;
+                    int loc[8], tot = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { loc[j] = s_hist[lane * 8 + j]; tot += loc[j]; }
+                    int above = tot;                 // inclusive suffix sum over lanes >= lane
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, above, o); if (lane + o < 32) above += t; }
+                    above -= tot;                    // keys in strictly higher lanes
+                    const int remaining = s_ctl[0];
+                    // the digit d with  count(> d) < remaining <= count(>= d)
+                    int cum = above, dsel = -1, need = 0, cnt = 0;
+#pragma unroll
+                    for (int j = 7; j >= 0; j--) {
+                        if (dsel < 0 && cum < remaining && cum + loc[j] >= remaining) { dsel = lane * 8 + j; need = remaining - cum; cnt = loc[j]; }
+                        cum += loc[j];
+                    }
+                    const unsigned hit = __ballot_sync(0xffffffffu, dsel >= 0);
+                    if (hit == 0) { if (lane == 0) { s_ctl[1] = 1; } }        // fewer valid keys than requested (cannot happen: m <= n valid): stop
+                    else if (lane == (int)(31 - __clz(hit))) {                  // the highest lane that found it
+                        s_prefix = prefix | ((unsigned long long)dsel << shift);
+                        s_ctl[0] = need;
+                        s_ctl[1] = (need == cnt) ? 1 : 0;                       // the whole bucket is needed: its lower bits need no refinement
+                    }
+                }
             }
-            __syncthreads();
-            remaining = s_misc[2];
+            cluster_sync_all();                      // rank 0 has published prefix / remaining / done
+            prefix = dsmem_ld_u64(r0_prefix);        // (rank 0 rewrites them only after the next pass's first cluster barrier)
+            const int done = dsmem_ld_i32(r0_ctl + 4);
+            if (done) break;
         }
-        const unsigned long long kth = s_prefix;  // keys are unique (seq unique) => exactly m keys >= kth
-        for (int i = threadIdx.x; i < P.sort_cap; i += SNT) { s_key[i] = 0ull; s_idx[i] = -1; }
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += SNT) {
+        kth = prefix;   // keys are unique (seq unique): exactly m keys are >= kth (lower bits zero when stopped early)
+    }
+    if (m > 0) {
+        if (rank == 0) {
+            for (int i = threadIdx.x; i < P.sort_cap; i += SNT) { s_key[i] = 0ull; s_idx[i] = -1; }
+        }
+        cluster_sync_all();
+        for (int i = (int)rank * SNT + threadIdx.x; i < n; i += SEL_CL * SNT) {
             const unsigned long long k = key_of(i);
             if (k >= kth && k != 0ull) {
-                const int pos = atomicAdd(&s_misc[3], 1);
-                if (pos < P.sort_cap) { s_key[pos] = k; s_idx[pos] = i; }
+                const int pos = dsmem_atomic_add(r0_fill, 1);
+                if (pos < P.sort_cap) { dsmem_st_u64(r0_key + (uint32_t)pos * 8u, k); dsmem_st_i32(r0_idx + (uint32_t)pos * 4u, i); }
             }
         }
-        __syncthreads();
+    }
+    cluster_sync_all();                              // the sort buffer of rank 0 is complete; the other CTAs are done
+    if (rank != 0) return;
+    if (m > 0) {
         if (threadIdx.x == 0 && s_misc[3] < s_misc[1]) s_misc[1] = s_misc[3];  // candidate list overflowed
+        __syncthreads();
         // bitonic sort, descending by key
         for (int k2 = 2; k2 <= P.sort_cap; k2 <<= 1) {
             for (int j = k2 >> 1; j > 0; j >>= 1) {
@@ -1062,11 +1122,13 @@ int ag_select_keypoints(const ag_pyramid_plan_t* p, const ag_detect_ws_t* ws, in
         set_error("ag_select_keypoints: selecting %d keypoints needs %zu B of shared memory (max 200 KiB)", need, smem);
         return AG_ERR_CAPACITY;
     }
-    static thread_local size_t configured = 0;
-    if (smem > 32 * 1024 && smem > configured) {  // static + dynamic must stay under the 48 KiB default
+    static size_t configured[64] = {};   // per device (the attribute is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 32 * 1024 && smem > configured[dev & 63]) {  // static + dynamic must stay under the 48 KiB default
         int rc = check_cuda(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "select smem attr");
         if (rc != AG_OK) return rc;
-        configured = smem;
+        configured[dev & 63] = smem;
     }
     SelectParams S;
     S.cand_val = ws->d_cand_val; S.cand_seq = ws->d_cand_seq; S.cand_scyx = ws->d_cand_scyx;
@@ -1074,7 +1136,15 @@ int ag_select_keypoints(const ag_pyramid_plan_t* p, const ag_detect_ws_t* ws, in
     S.cand_cap = ws->cand_cap; S.n_slots = ws->n_level_slots; S.n_det = p->n_levels - 2;
     S.num_features = num_features; S.out_cap = out_cap; S.sort_cap = sort_cap; S.a_scale = a_scale;
     S.resp = d_resp; S.lafs = d_lafs; S.oct = d_oct; S.lvl = d_lvl; S.count = d_count;
-    select_kernel<<<ws->B, SNT, smem, (cudaStream_t)stream>>>(S);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(ws->B * SEL_CL); cfg.blockDim = dim3(SNT); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = SEL_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int rcl = check_cuda(cudaLaunchKernelEx(&cfg, select_kernel, S), "select_kernel launch");
+    if (rcl != AG_OK) return rcl;
     AG_CHECK_LAUNCH("select_kernel");
     return AG_OK;
 }
