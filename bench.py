@@ -225,28 +225,38 @@ STENCIL = ("blur_kernel", "octave_kernel", "pyramid_tail_kernel", "detect_level_
 class Workload:
     """One configuration on this rank's GPU: pipeline, inputs, device-resident and end-to-end timed legs."""
 
-    def __init__(self, ctx, H, W, K, border, B, use_graph):
+    def __init__(self, ctx, H, W, K, border, B, use_graph, exchange=True):
         from affnet_b200.pipeline import DetectDescribePipeline
         self.ctx, self.H, self.W, self.K, self.border, self.B, self.use_graph = ctx, H, W, K, border, B, use_graph
         dev, rank, world = ctx["dev"], ctx["rank"], ctx["world"]
         a, o, h = ctx["nets"]
-        self.pipe = DetectDescribePipeline(B, H, W, a, h, o, num_features=K, border=border, do_ori=True, device=dev)
+        self.xchg = None
+        if world > 1 and exchange:
+            from affnet_b200.exchange import make_exchange
+            self.xchg, ctx["exchange_kind"] = make_exchange(world, B, K, dev)   # one gather per step, overlapped with the next step; the kernels write its blocks directly
+        self.pipe = DetectDescribePipeline(B, H, W, a, h, o, num_features=K, border=border, do_ori=True, device=dev,
+                                           outputs=self.xchg.outputs() if self.xchg else None)
         self.host_imgs = make_images(B, 1234 + rank * B, H, W).pin_memory()
         self.dev_imgs = self.host_imgs.to(dev)
-        self.xchg = None
-        if world > 1:
-            from affnet_b200.exchange import DescriptorExchange
-            self.xchg = DescriptorExchange(world, B, K, dev)   # one all-gather per step, overlapped with the next step
         self.last = [None, None, None, None]
+        self.step_i = 0
         if use_graph:
             self.pipe.capture()
 
-    def step_device(self):
-        out = self.pipe.replay(self.dev_imgs) if self.use_graph else self.pipe.run(self.dev_imgs)
+    def _run(self, imgs):
+        """One step into the next output slot; with an exchange: wait for the gather that last read the slot, compute, queue its gather."""
+        slot = (self.step_i & 1) if self.xchg else 0
         if self.xchg:
-            self.xchg.submit(out[0], out[2], out[3])
+            self.xchg.wait_slot(slot)
+        out = self.pipe.replay(imgs, slot) if self.use_graph else self.pipe.run(imgs, slot)
+        if self.xchg:
+            self.xchg.submit(slot)
+        self.step_i += 1
         self.last[:] = out
         return out
+
+    def step_device(self):
+        return self._run(self.dev_imgs)
 
     def timed(self, steps, warmup, sampler=None):
         ctx = self.ctx
@@ -295,7 +305,7 @@ class Workload:
         self.xchg.drain(); torch.cuda.synchronize()
         gd, gl, gc = self.xchg.last()
         own = slice(rank * B, (rank + 1) * B)
-        if not (torch.equal(gc[own], self.pipe.count.int()) and bool((gc > 0).all()) and torch.equal(gd[own], self.last[2]) and torch.equal(gl[own], self.last[0])):
+        if not (torch.equal(gc[own], self.last[3].int()) and bool((gc > 0).all()) and torch.equal(gd[own], self.last[2]) and torch.equal(gl[own], self.last[0])):
             raise RuntimeError("all-gather returned something else than this rank's results")
 
     def timed_e2e(self, steps, warmup):
@@ -331,9 +341,7 @@ class Workload:
             ev_free = torch.cuda.Event(); ev_free.record(cur)
             up_stream.wait_event(ev_free)                     # the other input slot was consumed by the previous step
             upload(slot ^ 1)                                  # next step's images travel while this step computes
-            out = pipe.replay(stage_in[slot]) if use_graph else pipe.run(stage_in[slot])
-            if xchg:
-                xchg.submit(out[0], out[2], out[3])
+            out = self._run(stage_in[slot])
             if i >= 2:
                 cur.wait_event(ev_done[slot])                 # the download that used this staging slot two steps ago has finished
             so = stage_out[slot]
@@ -374,7 +382,7 @@ class Workload:
         self.check_exchange()
         world = self.ctx["world"]
         pix = world * self.B * self.H * self.W
-        n_desc = int(self.pipe.count.sum().item())
+        n_desc = int(self.last[3].sum().item())
         ms = total_ms / steps
         out = {"workload": "%dx%d, %d kpts/img, border %d, %d image(s) per GPU per step" % (self.W, self.H, self.K, self.border, self.B),
                "value": pix / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": ms, "kpatches_per_s": world * n_desc / (ms * 1e-3) / 1e3, "steps": steps}
@@ -443,7 +451,7 @@ def _main(real_stdout):
     total_ms, clocks = wl.timed(args.steps, args.warmup, sampler)
     pipe.check()
     wl.check_exchange()
-    n_desc = int(pipe.count.sum().item())
+    n_desc = int(wl.last[3].sum().item())
     e2e_ms = wl.timed_e2e(args.steps, args.warmup)
 
     # ---- per-kernel CUDA-event profile of the same step (non-graph launch path), rank 0 ---------------------------
@@ -486,9 +494,18 @@ def _main(real_stdout):
             roof["stencil"]["frac"] = roof["stencil"]["achieved"] / pk["hbm"]
 
     launches_per_step = pipe.launches
+    exchange_cost = None
+    if world > 1:    # the same steps without the all-gather: what the exchange costs
+        wl.close(); wl = None; pipe = None
+        w0 = Workload(ctx, H, W, K, border, B, use_graph, exchange=False)
+        t0, _ = w0.timed(args.steps, args.warmup)            # same step and warm-up counts: the clocks sag over a long run, so the legs must be alike
+        w0.close(); w0 = None
+        exchange_cost = {"ms_per_step_without_exchange": t0 / args.steps, "ms_per_step_with_exchange": total_ms / args.steps,
+                         "kind": ctx.get("exchange_kind")}
     extra = None
     if not args.no_extras and args.config == "2" and not args.batch:
-        wl.close(); wl = None; pipe = None
+        if wl is not None:
+            wl.close(); wl = None; pipe = None
         extra = {}
         plan = [("b1", "2", 1, 10), ("b64_config4_shard", "2", 64, 3)] if world > 1 else [("b1", "2", 1, 10), ("b64_config4_shard", "2", 64, 3), ("config3", "3", 64, 2), ("config5", "5", 1, 5)]
         for name, cfg, b, st in plan:
@@ -525,7 +542,8 @@ def _main(real_stdout):
                 "data": "synthetic images (seeded noise, blur sigma 2, stretched), pretrained weights from tests/golden",
                 "config": {"workload": "%dx%d grayscale, %d kpts/img, batch of %d images per GPU per step (%s)" % (W, H, K, B, label),
                            "do_ori": True, "border": border, "mrSize": 5.192, "cuda_graph": use_graph, "l2": "256 MiB flush write between timed steps (device-resident leg); e2e leg: fresh inputs arrive by DMA every step, no flush",
-                           "parallelism": "images sharded across GPUs, one NCCL all-gather of descriptors+LAFs+counts per step, overlapped with the next step's compute" if world > 1 else "single GPU"},
+                           "parallelism": ("images sharded across GPUs, one all-gather of descriptors+LAFs+counts per step (%s), written by the kernels straight into the send block, overlapped with the next step's compute"
+                                           % {"ce": "peer-to-peer copy-engine pushes into symmetric memory + barrier", "nccl": "NCCL all_gather_into_tensor"}.get(ctx.get("exchange_kind"), "?")) if world > 1 else "single GPU"},
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "e2e": {"value": e2e_v, "unit": "Mpix/s", "h2d_bytes_per_step": B * H * W * 4,
                         "d2h_bytes_per_step": B * K * (128 + 6 + 1) * 4 + B * 4, "ms_per_step": e2e_ms / args.steps},
@@ -533,6 +551,8 @@ def _main(real_stdout):
                 "descriptors_per_step": world * n_desc}
         if extra is not None:
             line["extra"] = extra
+        if exchange_cost is not None:
+            line["exchange"] = exchange_cost
         emit(real_stdout, line)
     if dist is not None:
         dist.destroy_process_group()

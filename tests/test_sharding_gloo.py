@@ -56,13 +56,18 @@ def _exchange_worker(rank, world, port, q):
     from affnet_b200.exchange import DescriptorExchange
     B, K = 3, 5
     x = DescriptorExchange(world, B, K, torch.device("cpu"))
+    outs = x.outputs()                                                # per slot: the (lafs, desc, count) views a producer writes directly
 
     def step_data(r, step):
         g = torch.Generator().manual_seed(100 * step + r)
         return torch.rand(B, K, 2, 3, generator=g), torch.rand(B, K, 128, generator=g), torch.randint(1, K + 1, (B,), generator=g, dtype=torch.int32)
 
-    for step in range(5):                                             # more steps than staging slots: slots are reused
-        x.submit(*step_data(rank, step))
+    for step in range(5):                                             # more steps than blocks: blocks are reused
+        slot = step & 1
+        x.wait_slot(slot)                                             # the gather that last read this block has finished
+        l, d, c = step_data(rank, step)
+        outs[slot][0].copy_(l); outs[slot][1].copy_(d); outs[slot][2].copy_(c)     # "the kernels write the block"
+        x.submit(slot)
     x.drain()
     gd, gl, gc = x.last()
     ok = True
