@@ -20,6 +20,11 @@ def match_snn(descriptors1, descriptors2, SNN_threshold=0.8):
     a, b = L.f32c(descriptors1, "descriptors1"), L.f32c(descriptors2, "descriptors2")
     n1, n2 = a.size(0), b.size(0)
     dev = a.device
+    if a.dim() != 2 or b.dim() != 2 or (n1 and n2 and a.size(1) != b.size(1)):
+        raise L.AffnetB200Error("match_snn: descriptors must be [n1,D] and [n2,D] with the same D")
+    if n1 == 0 or n2 == 0:     # the reference returns empty matches
+        e = torch.empty(0, dtype=torch.long, device=dev)
+        return e, e.clone(), torch.empty(n1, device=dev), torch.empty(n1, device=dev)
     nb = L.lib().ag_match_snn_workspace_bytes(n1, n2)
     ws = torch.empty(nb, dtype=torch.uint8, device=dev)
     idx = torch.empty(n1, dtype=torch.int32, device=dev)

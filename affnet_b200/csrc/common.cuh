@@ -38,6 +38,21 @@ void prof_mark(const char* name);  // records an event after a launch when profi
         }                                                            \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember per device what was set (a process may drive several GPUs)
+struct SmemAttrOnce {
+    size_t set[64] = {};
+    template <typename K>
+    int ensure(K kernel, size_t bytes, const char* what) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (bytes <= set[dev]) return AG_OK;
+        int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), what);
+        if (rc == AG_OK) set[dev] = bytes;
+        return rc;
+    }
+};
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

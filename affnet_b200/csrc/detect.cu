@@ -1024,12 +1024,8 @@ int ag_detect(const ag_pyramid_plan_t* p, const float* d_pyr, float th, int mr_b
             return AG_OK;
         }
         constexpr size_t fsmem = sizeof(float) * (5 * PW * (PW + 1) + 5 * RW * (RW + 1));
-        static bool configured = false;
-        if (!configured) {
-            rc = check_cuda(cudaFuncSetAttribute(detect_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem), "detect smem attr");
-            if (rc != AG_OK) return rc;
-            configured = true;
-        }
+        static SmemAttrOnce attr_once;
+        if ((rc = attr_once.ensure(detect_fused_kernel, fsmem, "detect smem attr")) != AG_OK) return rc;
         detect_fused_kernel<<<dim3(tiles, p->B), DNT, fsmem, st>>>(F);
         AG_CHECK_LAUNCH("detect_fused_kernel");
         resolve_kernel<<<dim3(8, p->B), 256, 0, st>>>(ws->d_variants, p->n_octaves, ws->cand_cap, ws->d_cand_count, ws->d_cand_val, ws->d_cand_aux,

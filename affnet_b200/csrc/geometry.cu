@@ -205,11 +205,10 @@ int ag_affine_shape_filter(const float* d_A, const float* d_resp, const float* d
         set_error("ag_affine_shape_filter: cap %d needs %zu B of shared memory (max 200 KiB)", cap, smem);
         return AG_ERR_CAPACITY;
     }
-    static thread_local size_t configured = 0;
-    if (smem > 32 * 1024 && smem > configured) {  // static + dynamic must stay under the 48 KiB default
-        int rc = check_cuda(cudaFuncSetAttribute(shape_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "shape smem attr");
+    static SmemAttrOnce attr_once;
+    if (smem > 32 * 1024) {  // static + dynamic must stay under the 48 KiB default
+        int rc = attr_once.ensure(shape_filter_kernel, smem, "shape smem attr");
         if (rc != AG_OK) return rc;
-        configured = smem;
     }
     ShapeParams P;
     P.A = d_A; P.resp = d_resp; P.lafs = d_lafs; P.oct = d_oct; P.lvl = d_lvl; P.count_in = d_count_in;

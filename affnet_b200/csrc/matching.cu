@@ -51,7 +51,7 @@ __global__ void row_min_kernel(const float* __restrict__ dist, int n1, int n2, f
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= n1) return;
     float best = INFINITY;
-    int bj = 0x7fffffff;
+    int bj = 0x7fffffff;   // stays so only when the lane saw nothing smaller than +inf (e.g. an all-NaN row): resolved to column 0 below
     for (int j = lane; j < n2; j += 32) {
         const float v = dist[(size_t)i * n2 + j];
         if (v < best) { best = v; bj = j; }
@@ -61,7 +61,10 @@ __global__ void row_min_kernel(const float* __restrict__ dist, int n1, int n2, f
         const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
         if (ov < best || (ov == best && oj < bj)) { best = ov; bj = oj; }
     }
-    if (lane == 0) { mn[i] = best; arg[i] = bj; colmask[bj] = 1; }
+    if (lane == 0) {
+        if (bj < 0 || bj >= n2) bj = 0;       // a row of NaNs has no minimum: never index colmask out of bounds
+        mn[i] = best; arg[i] = bj; colmask[bj] = 1;
+    }
 }
 
 // per row: minimum after `dist[:, idxs] = 100000`, then the ratio test

@@ -136,12 +136,11 @@ template <int CIN, int COUT, int HIN, int STRIDE, int CT, int CK, bool NORM>
 static int launch_conv(const float* in, float* out, const float* w, const float* b, int n, int group, const int* count,
                        cudaStream_t st) {
     constexpr size_t smem = sizeof(float) * ((size_t)CIN * (HIN + 2) * (HIN + 2) + 9 * CK * CT);
-    static bool configured = false;
+    static SmemAttrOnce attr_once;
     auto kern = conv3x3_kernel<CIN, COUT, HIN, STRIDE, CT, CK, NORM>;
-    if (!configured) {
-        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv smem attr");
+    {
+        int rc = attr_once.ensure(kern, smem, "conv smem attr");
         if (rc != AG_OK) return rc;
-        configured = true;
     }
     kern<<<dim3(n, COUT / CT), CNT, smem, st>>>(in, out, w, b, group, count);
     AG_CHECK_LAUNCH("conv3x3_kernel");

@@ -34,11 +34,10 @@ static int launch_tc(const __half* in, void* out, const __half* w, const float* 
                      const FirstSrc* src = nullptr) {
     using Cfg = ConvCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, FIRST>;
     auto kern = tc_conv_kernel<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, FIRST>;
-    static bool configured = false;
-    if (!configured) {
-        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM), "tc_conv smem attr");
+    static SmemAttrOnce attr_once;
+    {
+        int rc = attr_once.ensure(kern, Cfg::SMEM, "tc_conv smem attr");
         if (rc != AG_OK) return rc;
-        configured = true;
     }
     ConvArgs a;
     a.in = in; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.prof_id = 0; a.n = n; a.group = group; a.count = count;
@@ -57,11 +56,10 @@ template <int C1, int COUT, int SA, int SW, int OSA>
 static int launch_first2(void* out, const __half* w, const float* b, float inv_scale, int n, int group, const int* count, cudaStream_t st, const FirstSrc& src) {
     using Cfg = FirstCfg<C1, COUT, SA, SW, OSA>;
     auto kern = tc_first2_kernel<C1, COUT, SA, SW, OSA>;
-    static bool configured = false;
-    if (!configured) {
-        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM), "tc_first2 smem attr");
+    static SmemAttrOnce attr_once;
+    {
+        int rc = attr_once.ensure(kern, Cfg::SMEM, "tc_first2 smem attr");
         if (rc != AG_OK) return rc;
-        configured = true;
     }
     ConvArgs a;
     a.in = nullptr; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.prof_id = 0; a.n = n; a.group = group; a.count = count;
@@ -78,11 +76,10 @@ template <int CIN, int COUT, int H, int STRIDE, int STAGES, int OUT>
 static int launch_pair(const __half* in, void* out, const __half* w, const float* b, float inv_scale, int n, int group, const int* count, cudaStream_t st) {
     using Cfg = PairCfg<CIN, COUT, H, STRIDE, STAGES, OUT>;
     auto kern = tc_conv_pair_kernel<CIN, COUT, H, STRIDE, STAGES, OUT>;
-    static bool configured = false;
-    if (!configured) {
-        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM), "tc_conv_pair smem attr");
+    static SmemAttrOnce attr_once;
+    {
+        int rc = attr_once.ensure(kern, Cfg::SMEM, "tc_conv_pair smem attr");
         if (rc != AG_OK) return rc;
-        configured = true;
     }
     ConvArgs a;
     a.in = in; a.out = out; a.wpk = w; a.bias = b; a.inv_scale = inv_scale; a.prof_id = 0; a.n = n; a.group = group; a.count = count;
@@ -162,12 +159,11 @@ int tc_hardnet_forward(const ag_net* net, const tc::FirstSrc& src0, int n, int g
 // HardNet 8x8 head GEMM + BatchNorm + L2 norm over the head operand a trunk left in `headbuf`
 int tc_hardnet_head(const ag_net* net, const void* headbuf, int n, int group, const int* count, float* out, cudaStream_t st, int bf16) {
     using namespace tc;
-    static bool configured = false;
-    if (!configured) {
-        int rc = check_cuda(cudaFuncSetAttribute(tc_head_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM), "tc_head smem attr");
-        if (rc == AG_OK) rc = check_cuda(cudaFuncSetAttribute(tc_head_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM), "tc_head smem attr");
+    static SmemAttrOnce once0, once1;
+    {
+        int rc = once0.ensure(tc_head_kernel<0>, HEAD_SMEM, "tc_head smem attr");
+        if (rc == AG_OK) rc = once1.ensure(tc_head_kernel<1>, HEAD_SMEM, "tc_head smem attr");
         if (rc != AG_OK) return rc;
-        configured = true;
     }
     if (bf16) tc_head_kernel<1><<<(n + 127) / 128, 192, HEAD_SMEM, st>>>((const __half*)headbuf, net->d_headh_bf, net->d_head_b, out, n, group, count);
     else tc_head_kernel<0><<<(n + 127) / 128, 192, HEAD_SMEM, st>>>((const __half*)headbuf, net->d_headh, net->d_head_b, out, n, group, count);
@@ -218,12 +214,11 @@ int tc_trunk_orinet(const ag_net* net, const tc::FirstSrc& src0, int n, int grou
 // AffNet / OriNet head on tensor cores over the hi/lo feature planes the trunks above leave in `feat`
 int tc_headx_forward(const ag_net* net, const void* feat, int n, int group, const int* count, float* out, float* angle, cudaStream_t st, float* raw) {
     using namespace tc;
-    static bool configured = false;
-    if (!configured) {
-        int rc = check_cuda(cudaFuncSetAttribute(tc_headx_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HX_SMEM), "tc_headx smem attr");
-        if (rc == AG_OK) rc = check_cuda(cudaFuncSetAttribute(tc_headx_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HX_SMEM), "tc_headx smem attr");
+    static SmemAttrOnce once0, once1;
+    {
+        int rc = once0.ensure(tc_headx_kernel<0>, HX_SMEM, "tc_headx smem attr");
+        if (rc == AG_OK) rc = once1.ensure(tc_headx_kernel<1>, HX_SMEM, "tc_headx smem attr");
         if (rc != AG_OK) return rc;
-        configured = true;
     }
     const int tiles = (n + 127) / 128;
     if (net->kind == AG_NET_AFFNET) tc_headx_kernel<0><<<tiles, 192, HX_SMEM, st>>>((const __half*)feat, net->d_headh, net->d_head_b, net->head_inv_scale, out, nullptr, raw, n, group, count);

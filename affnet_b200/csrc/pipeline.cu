@@ -33,6 +33,12 @@ int ag_pipeline_create(const ag_pipeline_config_t* cfg, const ag_net_t* affnet, 
     int rc = ag_pyramid_plan(cfg->B, cfg->H, cfg->W, cfg->nlevels, cfg->init_sigma, cfg->border, &p->plan);
     if (rc != AG_OK) { delete p; return rc; }
     p->M = (int)(1.5 * cfg->num_features);  // SparseImgRepresenter.py:194
+    if (p->M > 16384) {   // the selection kernels sort in shared memory (ag_select_keypoints / ag_affine_shape_filter): fail here, not at run time
+        set_error("ag_pipeline_create: num_features %d needs a prefilter of int(1.5 K) = %d keypoints; the shared-memory selection holds 16384 (K <= 10922)",
+                  cfg->num_features, p->M);
+        delete p;
+        return AG_ERR_CAPACITY;
+    }
     p->cand_cap = cfg->cand_cap > 0 ? cfg->cand_cap : (cfg->H * cfg->W) / 8;
     if (p->cand_cap < p->M) p->cand_cap = p->M;
     const size_t B = cfg->B, M = p->M, K = cfg->num_features;

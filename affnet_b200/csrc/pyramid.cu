@@ -198,13 +198,9 @@ static int launch_blur(const float* in, float* out, float* dec, int B, int h, in
     switch (taps.r) {
 #define AG_BLUR_CASE(R)                                                                                                   \
     case R: {                                                                                                             \
-        static bool configured = false;                                                                                   \
-        if (!configured) {                                                                                                \
-            rc = check_cuda(cudaFuncSetAttribute(blur_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BlurGeom<R>::SMEM), \
-                            "blur smem attr");                                                                            \
-            if (rc != AG_OK) return rc;                                                                                   \
-            configured = true;                                                                                            \
-        }                                                                                                                 \
+        static SmemAttrOnce attr_once;                                                                                    \
+        rc = attr_once.ensure(blur_kernel<R>, BlurGeom<R>::SMEM, "blur smem attr");                                       \
+        if (rc != AG_OK) return rc;                                                                                       \
         blur_kernel<R><<<grid, block, BlurGeom<R>::SMEM, st>>>(in, out, dec, h, w, taps);                                  \
     } break;
         AG_BLUR_CASE(1) AG_BLUR_CASE(2) AG_BLUR_CASE(3) AG_BLUR_CASE(4) AG_BLUR_CASE(5) AG_BLUR_CASE(6)
