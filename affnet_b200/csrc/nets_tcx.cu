@@ -3,8 +3,9 @@
 // architectures.py:207-235 / 36-82 and HardNet.py:67-101 (BatchNorm folded, ReLU fused); the 8x8 heads stay the GEMM kernels of
 // tc_head.cuh (same head-operand layout).  Per net:  tcx_first_kernel (sampler + input_norm + conv1 + conv2)  ->  tcx_conv_kernel x4.
 // Numerics: AffNet / OriNet with fp16 residual planes of weights and activations in every layer (three MMAs per K step, fp32-grade);
-// HardNet fp16 activations, weights with their fp16 residual in layers 2-4 (measured in emulation on the 2000 graf patches: the
-// descriptor error of plain fp16 weights is 1.1e-3, dominated by the weight rounding of layers 2-4; with their residuals 4e-4).
+// HardNet fp16 activations, weights with their fp16 residual in layers 2 and 3 (emulation on the 2000 graf patches: plain fp16 weights give a
+// descriptor error of 1.1e-3, dominated by the weight rounding of the early layers; measured on the GPU with the residuals of layers 2-3:
+// <= 4.9e-4 end to end over every parity configuration; adding layer 4's residual buys 0.5e-4 for 0.29 ms per step, layer 3's is free: HBM bound).
 #include <stdlib.h>
 #include <string.h>
 
@@ -141,8 +142,14 @@ void tcx_pack_layer(const float* wf, int ci, int co, int stride, int nsplit, int
 }
 
 int tcx_nsplit(int kind, int layer) { return (kind == AG_NET_HARDNET && layer >= 4) ? 2 : 1; }
-// weight residual copies: AffNet / OriNet every layer; HardNet layers 2-4 (layer index 1..3)
-int tcx_split_w(int kind, int layer) { return kind == AG_NET_HARDNET ? (layer <= 3 ? 1 : 0) : 1; }
+// weight residual copies: AffNet / OriNet every layer; HardNet layers 2-3 (layer index 1..2; see the A/B switches)
+#ifndef AG_HARD_SW3
+#define AG_HARD_SW3 1   // HardNet layer 3 / layer 4 weight residuals (A/B switches for the accuracy / time trade)
+#endif
+#ifndef AG_HARD_SW4
+#define AG_HARD_SW4 0   // measured r02: without it the worst descriptor error over all parity configurations is 4.9e-4 (with: 4.4e-4) and layer 4 is 0.29 ms per step faster
+#endif
+int tcx_split_w(int kind, int layer) { return kind == AG_NET_HARDNET ? (layer == 1 ? 1 : layer == 2 ? AG_HARD_SW3 : layer == 3 ? AG_HARD_SW4 : 0) : 1; }
 int tcx_stride(int layer) { return (layer == 2 || layer == 4) ? 2 : 1; }
 
 // bytes of each of the two ping-pong activation buffers for n patches (largest layer output: 64 KiB per patch; pair layouts round n up)
@@ -178,9 +185,9 @@ static int trunk_hardnet_t(const ag_net* net, const tc::FirstSrc& src0, int n, i
     int rc;
     if ((rc = launch_first<32, 32, 0, 1, 0, BF>(bufB, wx[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src))) return rc;
     if (upto <= 2) return AG_OK;
-    if ((rc = launch_conv<32, 64, 32, 2, 1, 2, L_S1_16, 0, 1, 0, 8, BF>(bufB, bufA, wx[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
+    if ((rc = launch_conv<32, 64, 32, 2, 1, 2, L_S1_16, 0, AG_HARD_SW3, 0, 8, BF>(bufB, bufA, wx[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
     if (upto <= 3) return AG_OK;
-    if ((rc = launch_conv<64, 64, 16, 1, 1, 2, L_S2_8P, 0, 1, 0, 8, BF>(bufA, bufB, wx[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
+    if ((rc = launch_conv<64, 64, 16, 1, 1, 2, L_S2_8P, 0, AG_HARD_SW4, 0, 8, BF>(bufA, bufB, wx[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
     if (upto <= 4) return AG_OK;
     if ((rc = launch_conv<64, 128, 16, 2, 2, 2, L_S1_8P, 0, 0, 0, 8, BF>(bufB, bufA, wx[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
     if (upto <= 5) return AG_OK;

@@ -33,7 +33,7 @@ CONFIGS = {   # BASELINE.json configs[...]: (H, W, K, border, default batch per 
 }
 ALG_BYTES_PER_PX = 30.66                      # detect stage, 4 B read + 5 levels x 4 B x 1.333 written
 FLOP_PER_PATCH = {"affnet": 19.19e6, "orinet": 19.32e6, "hardnet": 78.18e6}   # 2*MAC, SURVEY.md §8(d)
-DTYPE = "fp16 operands (fp16 residual planes: AffNet/OriNet weights+activations, HardNet layer 2-4 weights), fp32 accumulate; stencils fp32"
+DTYPE = "fp16 operands (fp16 residual planes: AffNet/OriNet weights+activations, HardNet layer 2-3 weights), fp32 accumulate; stencils fp32"
 
 
 def oracle_module():
@@ -476,7 +476,7 @@ def _main(real_stdout):
         tc_ms = sum(t for t, n, k in agg if k in TC_FAMILY)
         tc_launches = sum(n for t, n, k in agg if k in TC_FAMILY)
         ach = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-        roof = {"kernel": "tcgen05 kernels (%d launches/step: %s; fp16 operands with fp16 residual planes for AffNet/OriNet and HardNet layers 2-4, fp32 accumulate in TMEM)"
+        roof = {"kernel": "tcgen05 kernels (%d launches/step: %s; fp16 operands with fp16 residual planes for AffNet/OriNet and HardNet layers 2-3, fp32 accumulate in TMEM)"
                           % (tc_launches, ", ".join("%s x%d" % (k, n) for t, n, k in agg if k in TC_FAMILY)),
                 "bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"],
                 "traffic": ncu_traffic(B), "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)", "kernel_ms_per_step": tc_ms,

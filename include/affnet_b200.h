@@ -169,7 +169,7 @@ size_t ag_net_blob_floats(int kind);
  * AffNet's A about 15x, so the 1e-3 LAF contract needs A to 5e-5), HardNet plain fp16 operands (descriptors 6e-4);
  * 2 = as 1 with fp32 FMA-chain heads (A 2e-6, angle 3e-6 rad; AffNet/OriNet only); 3 = AffNet with the weight residual only
  * (A 2e-4; for A/B timing, AffNet only);
- * 4 = second-generation tcgen05 engine (same operand precision as 1, plus fp16 residuals of HardNet's layer 2-4 weights): 128-pixel
+ * 4 = second-generation tcgen05 engine (same operand precision as 1, plus fp16 residuals of HardNet's layer 2-3 weights): 128-pixel
  * row tiles without x padding, the three taps of a kernel row stacked along N of one MMA, x shifts by warp shuffles in the epilogue;
  * 5 = engine 4 with bf16 operands (HardNet only; BASELINE.json configs[4] "bf16 HardNet tensor-core path"; descriptors ~4e-3). */
 int ag_net_set_engine(ag_net_t* net, int engine);

@@ -582,10 +582,10 @@ def circular_gauss_kernel(kernlen, sigma=None):
     return k / np.sum(k)
 
 
-def orientation_hist(patches, num_bins=36):
-    """OrientationDetector.forward (HandCraftedModules.py:168-192), returns the angle [n].
+def orientation_hist_bins(patches, num_bins=36):
+    """The smoothed 36-bin histogram of OrientationDetector.forward (HandCraftedModules.py:168-190) -> [n,36].
     gx/gy = (0.5,0,-0.5) cross-correlations with replicate padding; only the lower-bin weight wo0 is accumulated (as the
-    reference does); smoothing (0.33,0.34,0.33) with ZERO padding; argmax; angle = -(2 pi idx/36 - pi)."""
+    reference does); smoothing (0.33,0.34,0.33) with ZERO padding."""
     PS = patches.size(2)
     x = patches
     xp = F.pad(x, (1, 1, 0, 0), "replicate")
@@ -601,8 +601,13 @@ def orientation_hist(patches, num_bins=36):
     bo0 = bo0 % num_bins
     wo0 = (1.0 - wo1) * mag
     bins = torch.stack([((bo0 == i).float() * wo0).mean(dim=(1, 2, 3)) for i in range(num_bins)], dim=1)   # [n,36]
-    sm = F.conv1d(bins.view(-1, 1, num_bins), torch.tensor([[[0.33, 0.34, 0.33]]]), padding=1).view(-1, num_bins)
-    idx = sm.max(1)[1]
+    return F.conv1d(bins.view(-1, 1, num_bins), torch.tensor([[[0.33, 0.34, 0.33]]]), padding=1).view(-1, num_bins)
+
+
+def orientation_hist(patches, num_bins=36):
+    """OrientationDetector.forward (HandCraftedModules.py:168-192), returns the angle [n]: argmax of the smoothed histogram;
+    angle = -(2 pi idx/36 - pi)."""
+    idx = orientation_hist_bins(patches, num_bins).max(1)[1]
     return -((2.0 * float(np.pi) * idx.float() / float(num_bins)) - float(math.pi))
 
 

@@ -466,7 +466,7 @@ def test_handcrafted_estimators_8f(L):
     ang = OrientationDetector(patch_size=19)(P.to(DEV)).cpu()
     ref = O.orientation_hist(P)
     agree = (torch.atan2(torch.sin(ang - ref), torch.cos(ang - ref)).abs() < 1e-5).float().mean().item()
-    assert agree >= 0.98, agree            # arg-max over fp32 bin sums: a near-tie may pick the neighbouring 10-degree bin
+    assert agree == 1.0, agree             # same patches -> same bins (r02 diagnostic scripts/ori_bins_diag.py: 200/200, no pixel changes its bin)
     A = AffineShapeEstimator(patch_size=19)(P.to(DEV)).cpu()
     assert (A - O.baumberg_shape(P)).abs().max() < 1e-4
     img = crop_img()
@@ -550,7 +550,23 @@ def test_graf_1_to_6_application_counts(L, nets, mode):
     _, keep, _ = O.gt_correspondences(L1[i1].cpu(), L2[i2].cpu(), torch.from_numpy(z["H1to6"]), float(z["px"]))
     tent, true = int(i1.numel()), int(keep.numel())
     print("\ngraf 1<->6 %s: %d tentatives / %d true (reference %d / %d)" % (mode, tent, true, int(z[mode + "_tent"]), int(z[mode + "_true"])))
-    # the gradient-histogram orientation is an arg-max over 36 bins: pyramid differences of 3e-4 flip a few of the 6000 keypoints to another
-    # bin, which changes their descriptors completely; the "true" count of the reference's loose check then moves by up to ~10 %
     assert abs(tent - int(z[mode + "_tent"])) <= max(4, 0.03 * int(z[mode + "_tent"]))
-    assert abs(true - int(z[mode + "_true"])) <= max(4, 0.1 * int(z[mode + "_true"]))
+    if mode != "hcori":
+        assert abs(true - int(z[mode + "_true"])) <= max(4, 0.05 * int(z[mode + "_true"]))
+        return
+    # Hand-crafted orientation = arg-max over 36 histogram bins.  The kernel reproduces the reference's bins exactly on identical patches
+    # (test_handcrafted_estimators_8f); end to end the separable blur's 3e-4 pyramid differences reach the 19x19 patches, and a keypoint
+    # whose two best bins are a near-tie then takes the other bin (10 degrees or more away: a different descriptor, which is what moves
+    # the loose "true" count).  Accounted for per keypoint: every keypoint whose orientation differs from the oracle's must be such a near-tie.
+    assert abs(true - int(z[mode + "_true"])) <= max(6, 0.08 * int(z[mode + "_true"]))
+    oL, _, st = O.detect(gray_from_rgb(f["rgb"]), W["affnet"], None, 3000, do_ori=True, debug=True)
+    sm = O.orientation_hist_bins(st["debug"]["ori"]["patches"])
+    top = sm.topk(2, dim=1).values
+    margin = (top[:, 0] - top[:, 1]) / top[:, 0]
+    ia, ib = match_keypoints(oL, L1.cpu())
+    eA = ((oL[ia][:, :, :2] - L1.cpu()[ib][:, :, :2]).abs().amax(dim=(1, 2)) / (oL[ia][:, 0, 0] * oL[ia][:, 1, 1] - oL[ia][:, 0, 1] * oL[ia][:, 1, 0]).abs().sqrt())
+    flipped = (eA > 1e-2).nonzero().view(-1)
+    print("img1: %d of %d matched keypoints take another orientation bin than the oracle; their top-2 bin margins (oracle): %s" % (
+        flipped.numel(), len(ia), ["%.1e" % margin[ia[i]].item() for i in flipped.tolist()]))
+    assert len(ia) >= 0.995 * oL.shape[0] and flipped.numel() <= 0.005 * len(ia)
+    assert all(margin[ia[i]].item() < 5e-3 for i in flipped.tolist())
