@@ -482,7 +482,7 @@ def _main(real_stdout):
                 "traffic": ncu_traffic(B), "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)", "kernel_ms_per_step": tc_ms,
                 "algorithmic_flop_per_step": tc_flop, "share_of_step": tc_ms / step_ms if step_ms else None,
                 "note": "algorithmic flops = 2*MAC of the reference's fp32 convolutions; the residual-plane products (3 MMAs per K step for AffNet/OriNet, 2 for HardNet "
-                        "layers 2-4) and the K=9 first layer padded to K=16 are extra tensor work that is not counted",
+                        "layers 2-3) and the K=9 first layer padded to K=16 are extra tensor work that is not counted",
                 "timing": "CUDA events after every launch over %d profiled steps right after the timed region" % prof_steps,
                 "stages_ms": {k: round(t, 4) for t, n, k in agg}, "launches_ms": order}
         # HBM roofline of the stencil side (pyramid + detect kernels), reported alongside

@@ -132,7 +132,7 @@ def test_raw_heads_vs_reference_torchscript(L):
 
 def test_hardnet_bf16_engine(L):
     """BASELINE.json configs[4] asks for a bf16 HardNet tensor-core path: engine 5 = the second-generation engine with bf16 operands
-    (activations bf16, weights bf16 + bf16 residual in layers 2-4, fp32 accumulate).  Own tolerance (SURVEY section 7 hard part 1: ~1e-2):
+    (activations bf16, weights bf16 + bf16 residual in layers 2-3, fp32 accumulate).  Own tolerance (SURVEY section 7 hard part 1: ~1e-2):
     bf16 keeps 8 mantissa bits, the emulation on the 2000 graf patches gives 1.6e-3 with exact weights and 7e-3 with plain bf16 weights."""
     from affnet_b200.HardNet import HardNet
     hn = HardNet(); hn.load_state_dict(W["hardnet"]); hn = hn.eval().to(DEV)
