@@ -69,6 +69,26 @@ __host__ __device__ inline uint32_t float_to_ordered(float f) {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// Block-wide bitonic sort (descending) of n = 2^k 64-bit keys in shared memory, optionally with an int payload.  Every thread owns whole
+// compare-exchange PAIRS (pair p -> elements i = p with a 0 bit inserted at log2(j), i | j), so no thread idles on the "ixj > i" half:
+// half the loop trips of the textbook form (select_kernel: 163 -> ~95 us for 4096 keys on 1024 threads).
+template <bool HAS_IDX>
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* key, int* idx, int n) {
+    for (int k2 = 2; k2 <= n; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int p = threadIdx.x; p < (n >> 1); p += blockDim.x) {
+                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i | j;
+                const unsigned long long a = key[i], c = key[l];
+                const bool desc = (i & k2) == 0;
+                if (desc ? (a < c) : (a > c)) {
+                    key[i] = c; key[l] = a;
+                    if (HAS_IDX) { const int t = idx[i]; idx[i] = idx[l]; idx[l] = t; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
 // Bilinear tap with zeros outside the image (F.grid_sample, padding_mode='zeros').  Explicit rounding steps so that the
 // standalone sampler and the sampler fused into the first CNN layer produce identical bits.
 __device__ __forceinline__ float bilinear_zero(const float* __restrict__ img, int h, int w, float px, float py) {

@@ -881,23 +881,7 @@ __global__ void __launch_bounds__(SNT) select_kernel(const SelectParams P) {
     if (m > 0) {
         if (threadIdx.x == 0 && s_misc[3] < s_misc[1]) s_misc[1] = s_misc[3];  // candidate list overflowed
         __syncthreads();
-        // bitonic sort, descending by key
-        for (int k2 = 2; k2 <= P.sort_cap; k2 <<= 1) {
-            for (int j = k2 >> 1; j > 0; j >>= 1) {
-                for (int i = threadIdx.x; i < P.sort_cap; i += SNT) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const unsigned long long a = s_key[i], c = s_key[ixj];
-                        const bool desc = (i & k2) == 0;
-                        if (desc ? (a < c) : (a > c)) {
-                            s_key[i] = c; s_key[ixj] = a;
-                            const int t = s_idx[i]; s_idx[i] = s_idx[ixj]; s_idx[ixj] = t;
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-        }
+        bitonic_sort_desc<true>(s_key, s_idx, P.sort_cap);   // descending by key
     }
     // outputs
     __syncthreads();

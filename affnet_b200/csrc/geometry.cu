@@ -96,18 +96,7 @@ __global__ void __launch_bounds__(GNT) shape_filter_kernel(const ShapeParams P) 
         s_key[i] = k;
     }
     __syncthreads();
-    for (int k2 = 2; k2 <= P.sort_cap; k2 <<= 1)
-        for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < P.sort_cap; i += GNT) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = s_key[i], c = s_key[ixj];
-                    const bool desc = (i & k2) == 0;
-                    if (desc ? (a < c) : (a > c)) { s_key[i] = c; s_key[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
+    bitonic_sort_desc<false>(s_key, nullptr, P.sort_cap);
     for (int r = threadIdx.x; r < m; r += GNT) {
         const int i = (int)(0xFFFFFFFFu - (unsigned)(s_key[r] & 0xFFFFFFFFull));
         const size_t o = (size_t)b * P.out_cap + r;

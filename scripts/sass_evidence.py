@@ -39,9 +39,9 @@ def main():
           "Instruction counts per kernel; made by `python scripts/sass_evidence.py %s` (no GPU needed)." % tag, "",
           "| kernel | SASS instr | " + " | ".join(PAT) + " |", "|---" * (len(PAT) + 2) + "|"]
     for k, c in kernels.items():
-        name = re.sub(r"^(void )?(ag::)?(tc::)?", "", demangle(k))
+        name = re.sub(r"^(void )?(ag::)?(tcx?::|pf::)?", "", demangle(k))
         name = re.sub(r"\(.*$", "", name)
-        if not any(c[p] for p in list(PAT)[:5]) and not name.startswith(("detect_warp", "blur")):
+        if not any(c[p] for p in list(PAT)[:5]) and not name.startswith(("detect_warp", "blur", "select_kernel", "octave")):
             continue
         md.append("| `%s` | %d | " % (name, c["_n"]) + " | ".join(str(c[p]) for p in PAT) + " |")
     open(os.path.join(ROOT, "profiles", tag + "_sass_evidence.md"), "w").write("\n".join(md) + "\n")
