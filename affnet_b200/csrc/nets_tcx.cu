@@ -143,13 +143,16 @@ void tcx_pack_layer(const float* wf, int ci, int co, int stride, int nsplit, int
 
 int tcx_nsplit(int kind, int layer) { return (kind == AG_NET_HARDNET && layer >= 4) ? 2 : 1; }
 // weight residual copies: AffNet / OriNet every layer; HardNet layers 2-3 (layer index 1..2; see the A/B switches)
+#ifndef AG_HARD_SW2
+#define AG_HARD_SW2 1
+#endif
 #ifndef AG_HARD_SW3
 #define AG_HARD_SW3 1   // HardNet layer 3 / layer 4 weight residuals (A/B switches for the accuracy / time trade)
 #endif
 #ifndef AG_HARD_SW4
 #define AG_HARD_SW4 0   // measured r02: without it the worst descriptor error over all parity configurations is 4.9e-4 (with: 4.4e-4) and layer 4 is 0.29 ms per step faster
 #endif
-int tcx_split_w(int kind, int layer) { return kind == AG_NET_HARDNET ? (layer == 1 ? 1 : layer == 2 ? AG_HARD_SW3 : layer == 3 ? AG_HARD_SW4 : 0) : 1; }
+int tcx_split_w(int kind, int layer) { return kind == AG_NET_HARDNET ? (layer == 1 ? AG_HARD_SW2 : layer == 2 ? AG_HARD_SW3 : layer == 3 ? AG_HARD_SW4 : 0) : 1; }
 int tcx_stride(int layer) { return (layer == 2 || layer == 4) ? 2 : 1; }
 
 // bytes of each of the two ping-pong activation buffers for n patches (largest layer output: 64 KiB per patch; pair layouts round n up)
@@ -183,7 +186,7 @@ static int trunk_hardnet_t(const ag_net* net, const tc::FirstSrc& src0, int n, i
     src.w1 = net->d_w1; src.b1 = net->d_b[0]; src.w1_inv = net->w_inv_scale[0]; src.w1_scale = 1.0f / net->w_inv_scale[0];
     __half* const* wx = BF ? net->d_wx_bf : net->d_wx;
     int rc;
-    if ((rc = launch_first<32, 32, 0, 1, 0, BF>(bufB, wx[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src))) return rc;
+    if ((rc = launch_first<32, 32, 0, AG_HARD_SW2, 0, BF>(bufB, wx[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src))) return rc;
     if (upto <= 2) return AG_OK;
     if ((rc = launch_conv<32, 64, 32, 2, 1, 2, L_S1_16, 0, AG_HARD_SW3, 0, 8, BF>(bufB, bufA, wx[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
     if (upto <= 3) return AG_OK;
