@@ -107,9 +107,34 @@ __global__ void __launch_bounds__(NT) blur_kernel(const float* __restrict__ in, 
     const float* img = in + (size_t)b * h * w;
     // 1. input window with replicate (clamp) addressing
 #ifndef AG_BLUR_SCALAR_FILL
-    // interior tiles fill the window with 128-bit loads (the scalar fill was 30 % of this kernel's stall samples); same values in
-    // the same places, so the arithmetic does not change
-    if ((w & 3) == 0 && x0 - R4 >= 0 && x0 - R4 + G::IW <= w && (reinterpret_cast<size_t>(img) & 15) == 0) {
+    // interior tiles: same values in the same places as the clamped fill below, so the arithmetic does not change
+    const bool wide = (w & 3) == 0 && x0 - R4 >= 0 && x0 - R4 + G::IW <= w && (reinterpret_cast<size_t>(img) & 15) == 0;
+#ifndef AG_BLUR_LDG_FILL
+    // ... and tiles that need no row clamp either take the window as IH bulk copies (one 16-byte-aligned row segment each, issued by
+    // warp 0, completion counted on one mbarrier): no thread spends issue slots or registers on the fill
+    __shared__ __align__(8) unsigned long long s_bar;
+    const bool bulk = wide && y0 - R >= 0 && y0 - R + G::IH <= h;    // block-uniform
+    if (bulk) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(G::IH * G::IW * 4)) : "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const float* src = img + (size_t)(y0 - R) * w + (x0 - R4);
+            for (int ly = threadIdx.x; ly < G::IH; ly += 32)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(s_in + ly * G::IW)),
+                             "l"(src + (size_t)ly * w), "r"((uint32_t)(G::IW * 4)), "r"(bar)
+                             : "memory");
+        }
+        asm volatile("{\n .reg .pred P;\n W_%=:\n mbarrier.try_wait.parity.shared::cta.b64 P, [%0], 0;\n @P bra D_%=;\n bra W_%=;\n D_%=:\n}\n" ::"r"(bar) : "memory");
+    } else
+#endif
+    // 128-bit loads (the scalar fill was 30 % of this kernel's stall samples)
+    if (wide) {
         constexpr int QW = G::IW / 4;
         static_assert(G::IW % 4 == 0, "window rows are whole float4s");
         for (int i = threadIdx.x; i < G::IH * QW; i += NT) {
