@@ -21,7 +21,7 @@ cap prof_blur -k "regex:blur_kernel" -s 75 -c 6 $B
 # stencil kernels (octave-0 blurs + detector)
 C3="python bench.py --config 3 --batch 16 --steps 1 --warmup 3 --no-cpu-baseline --no-graph --no-extras"
 ncu --metrics gpu__time_duration.sum --clock-control none -s 156 -c 52 --csv --log-file gpurun_out/launches_c3.csv $C3 > gpurun_out/ncu_bench_c3.log 2>&1
-cap prof_c3_blur -k "regex:blur_kernel" -s 75 -c 5 $C3
+cap prof_c3_blur -k "regex:blur_kernel" -s 87 -c 5 $C3
 cap prof_c3_detect -k "regex:detect_warp_kernel" -s 3 -c 1 $C3
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 ls -la gpurun_out; du -sh gpurun_out

@@ -111,6 +111,82 @@ static void run_mma_row(long long* d_out, int smem) {
            run_mma<MODE, M, 256>(d_out, smem));
 }
 
+
+// The same issue loop from NI issuer threads (one per warp, warps 1 .. NI) running concurrently, each into its own accumulator columns
+// and with its own completion barrier: does the small-N floor belong to the issuing thread or to the tensor pipe?
+// out[0] = cycles from the earliest start to the latest completion; every issuer issues the full 288 MMAs.
+template <int NI, int N>
+__global__ void __launch_bounds__(192) mma_rate_multi(long long* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar[4];
+    __shared__ uint32_t tmem_base;
+    __shared__ long long t_begin[4], t_end[4];
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + 2 * NPIX * 16;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (2 * NPIX * 16 + 9 * 2 * 256 * 16) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base;
+    if ((threadIdx.x & 31) == 0 && warp >= 1 && warp <= NI) {
+        const int me = warp - 1;
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a_lo = desc_lo(smem_u32(sA), NPIX * 16u), b_lo = desc_lo(smem_u32(sB), 256 * 16u);
+        const uint32_t dbase = tmem + (uint32_t)(me * 128);          // N <= 64: two buffers of 64 columns per issuer
+        for (int rep = 0; rep < 3; rep++) {
+            const long long t0 = clock64();
+#pragma unroll 1
+            for (int round = 0; round < 4; round++) {
+#pragma unroll
+                for (int tile = 0; tile < 8; tile++) {
+                    const uint32_t d = dbase + (uint32_t)((tile & 1) * 64);
+#pragma unroll
+                    for (int tap = 0; tap < 9; tap++) {
+                        const uint32_t alo = a_lo + (uint32_t)(tile * 128 + (tap / 3) * 34 + tap % 3);
+                        const uint32_t blo = b_lo + (uint32_t)(tap * 2 * 256);
+                        umma_ss(d, alo, blo, idesc, tap > 0);
+                    }
+                }
+            }
+            umma_commit(smem_u32(&bar[me]));
+            mbar_wait(smem_u32(&bar[me]), rep & 1);
+            const long long t1 = clock64();
+            if (rep == 2) { t_begin[me] = t0; t_end[me] = t1; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long b = t_begin[0], e = t_end[0];
+        for (int w = 1; w < NI; w++) { b = min(b, t_begin[w]); e = max(e, t_end[w]); }
+        out[0] = e - b;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+template <int NI, int N>
+static double run_multi(long long* d_out, int smem) {
+    CK(cudaFuncSetAttribute(mma_rate_multi<NI, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mma_rate_multi<NI, N><<<1, 192, smem>>>(d_out);
+    CK(cudaDeviceSynchronize());
+    long long c;
+    CK(cudaMemcpy(&c, d_out, 8, cudaMemcpyDeviceToHost));
+    return (double)c / (4 * 8 * 9 * NI);     // clk per MMA of the SM (all issuers together)
+}
+
 template <int X>
 __device__ __forceinline__ uint32_t tmem_ld_sum(uint32_t taddr);
 template <>
@@ -252,6 +328,10 @@ int main() {
     run_mma_row<0, 64>(d_out, smem);
     run_mma_row<1, 128>(d_out, smem);
     run_mma_row<1, 64>(d_out, smem);
+    printf("== the same from 1 / 2 / 4 issuer warps at once (M=128, SS): clk per MMA of the SM\n");
+    printf("  N=16: 1 issuer %.1f | 2 issuers %.1f | 4 issuers %.1f\n", run_multi<1, 16>(d_out, smem), run_multi<2, 16>(d_out, smem), run_multi<4, 16>(d_out, smem));
+    printf("  N=48: 1 issuer %.1f | 2 issuers %.1f | 4 issuers %.1f\n", run_multi<1, 48>(d_out, smem), run_multi<2, 48>(d_out, smem), run_multi<4, 48>(d_out, smem));
+    printf("  N=64: 1 issuer %.1f | 2 issuers %.1f | 4 issuers %.1f\n", run_multi<1, 64>(d_out, smem), run_multi<2, 64>(d_out, smem), run_multi<4, 64>(d_out, smem));
     printf("== tcgen05.ld 32x32b: bytes per clk per SM\n");
     for (int nw : {1, 2, 4, 8, 16}) {
         long long c32, c64;
