@@ -654,6 +654,234 @@ __global__ void __launch_bounds__(WNT) detect_warp_kernel(const WarpParams P) {
     }
 }
 
+// ======================================================================================================================
+// Same detector, rows in registers (r02; ncu source view of detect_warp_kernel: 691 warp instructions per row, of which 155 issue the
+// next row's cp.async through divergent halo branches and dynamically indexed constant loads, 45 re-read the 3x3 pyramid windows from
+// shared memory, 40 rotate state registers, ~90 are the lone-lane soft-argmax divisions):
+//   * every pyramid row is read from the ring ONCE (3 LDS per level); what later rows need of it stays in registers: the centre, the
+//     half difference 0.5 l - 0.5 r (the gxy term of the rows above / below) and (l - 2 c) + r (gxx of the row itself) - the same
+//     float operations in the same order as hessian_regs, so the response is bit-identical;
+//   * the row loop is unrolled by three with compile-time slot indices: no register rotation;
+//   * the row fetch is branch-free: one cp.async per level from a per-lane offset, the two halo columns by a predicated second one;
+//   * the soft-argmax divisions move to the candidate flush, where 32 lanes finish 32 candidates at once.
+// Records, counters and their semantics are those of detect_warp_kernel / detect_fused_kernel.
+// ======================================================================================================================
+template <int I> struct IC { static constexpr int value = I; };
+
+template <int OFF>
+__device__ __forceinline__ void cp_async4_off(uint32_t dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0 + %2], [%1], 4;" ::"r"(dst), "l"(src), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void cp_async4_off_if(uint32_t dst, const float* src, bool p) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q cp.async.ca.shared.global [%0 + %2], [%1], 4;\n}\n" ::"r"(dst), "l"(src), "n"(OFF), "r"((uint32_t)p)
+                 : "memory");
+}
+
+constexpr int RCB = 10;   // staged candidate record: val, n1, n2, seq, ns, ny, nx, den, y, x
+
+__global__ void __launch_bounds__(WNT, 3) detect_rows_kernel(const WarpParams P) {
+    __shared__ float s_ring[WNT / 32][WRING][5][WROWLEN];
+    __shared__ float s_cbuf[WNT / 32][RCB][WCBUF];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int u = blockIdx.x * (WNT / 32) + wib;
+    if (u >= P.total_units) return;
+    int oi = 0;
+#pragma unroll 1
+    for (int i = 1; i < P.n_oct; i++)
+        if (u >= P.oct[i].unit_base) oi = i;
+    u -= P.oct[oi].unit_base;
+    // octave constants into registers (dynamically indexed kernel parameters are constant-bank loads at every use otherwise)
+    const float* lvl[5];
+    float s4[5], sc[5];
+#pragma unroll
+    for (int d = 0; d < 5; d++) { lvl[d] = P.oct[oi].lvl[d]; s4[d] = P.oct[oi].s4[d]; sc[d] = P.oct[oi].sc[d]; }
+    const int h = P.oct[oi].h, w = P.oct[oi].w, strips_x = P.oct[oi].strips_x;
+    const float th = P.th;
+    const int b = blockIdx.y;
+    const int band = u / strips_x, strip = u - band * strips_x;
+    const int r0 = band * WROWS;
+    const int gx = strip * WCOLS - 1 + lane;            // lane's column; lanes 0 / 31 are the response halo
+    const bool col_in = gx >= 0 && gx < w;
+    const int cx = clampi(gx, 0, w - 1);
+    const bool halo_lane = lane == 0 || lane == 31;
+    const int hdelta = (lane == 0 ? clampi(gx - 1, 0, w - 1) : clampi(gx + 1, 0, w - 1)) - cx;   // extra column of the halo lanes
+    const int base_off = b * h * w + cx;                 // < 2^31: a level of the whole batch is indexed with int elsewhere too
+    const bool border_ok = (P.mr_border < w) && (P.mr_border < h);
+    const bool col_ok = lane >= 1 && lane <= WCOLS && col_in && border_ok && gx >= P.mr_border && gx < w - P.mr_border;
+    const int rows_out = min(WROWS, h - r0);
+    const int n_rows = rows_out + 4;                     // pyramid rows r0-2 .. r0+rows_out+1
+    float (*ring)[5][WROWLEN] = s_ring[wib];
+    const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(&ring[0][0][lane + 1]);
+    const uint32_t sdst_h = (lane == 0) ? sdst - 4u : sdst + 4u;   // halo lanes: column 0 / 33
+
+    auto issue_row = [&](int c) {                        // pyramid row r0-2+c -> ring slot c % WRING (replicate-clamped)
+        if (c < n_rows) {
+            const int cy = clampi(r0 - 2 + c, 0, h - 1);
+            const int off = base_off + cy * w;
+            const uint32_t so = (uint32_t)((c % WRING) * (5 * WROWLEN * 4));
+            cp_async4_off<0 * WROWLEN * 4>(sdst + so, lvl[0] + off); cp_async4_off_if<0 * WROWLEN * 4>(sdst_h + so, lvl[0] + off + hdelta, halo_lane);
+            cp_async4_off<1 * WROWLEN * 4>(sdst + so, lvl[1] + off); cp_async4_off_if<1 * WROWLEN * 4>(sdst_h + so, lvl[1] + off + hdelta, halo_lane);
+            cp_async4_off<2 * WROWLEN * 4>(sdst + so, lvl[2] + off); cp_async4_off_if<2 * WROWLEN * 4>(sdst_h + so, lvl[2] + off + hdelta, halo_lane);
+            cp_async4_off<3 * WROWLEN * 4>(sdst + so, lvl[3] + off); cp_async4_off_if<3 * WROWLEN * 4>(sdst_h + so, lvl[3] + off + hdelta, halo_lane);
+            cp_async4_off<4 * WROWLEN * 4>(sdst + so, lvl[4] + off); cp_async4_off_if<4 * WROWLEN * 4>(sdst_h + so, lvl[4] + off + hdelta, halo_lane);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // per level and slot (slot = row index mod 3): pyramid-row terms pc (centre), ph (0.5 l - 0.5 r), pg ((l - 2 c) + r), and of the
+    // response rows: response, horizontal 3-max, horizontal sums for the soft-argmax (sum r, sum x_off * r)
+    float pc[5][3], ph[5][3], pg[5][3], rs[5][3], rmx[5][3], hs[5][3], hx[5][3];
+#pragma unroll
+    for (int d = 0; d < 5; d++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) { pc[d][q] = 0.f; ph[d][q] = 0.f; pg[d][q] = 0.f; rs[d][q] = 0.f; rmx[d][q] = 0.f; hs[d][q] = 0.f; hx[d][q] = 0.f; }
+    int var[14];
+#pragma unroll
+    for (int i = 0; i < 14; i++) var[i] = 0;
+    const float min_size = (float)min(h, w);
+    const float fh = (float)h, fw = (float)w;
+
+    int buf_n = 0;   // warp-uniform
+    float (*cbuf)[WCBUF] = s_cbuf[wib];
+    auto flush = [&]() {
+        if (buf_n == 0) return;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&P.cand_count[b], buf_n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (int i = lane; i < buf_n; i += 32) {
+            const int dst = base + i;
+            if (dst < P.cand_cap) {
+                const size_t o = (size_t)b * P.cand_cap + dst;
+                const float ns = cbuf[4][i], ny = cbuf[5][i], nx = cbuf[6][i], den = cbuf[7][i];
+                P.cand_val[o] = cbuf[0][i];
+                P.cand_aux[o * 2 + 0] = cbuf[1][i];
+                P.cand_aux[o * 2 + 1] = cbuf[2][i];
+                P.cand_seq[o] = __float_as_uint(cbuf[3][i]);
+                P.cand_scyx[o * 3 + 0] = __fdiv_rn(__fdiv_rn(ns, den), min_size);
+                P.cand_scyx[o * 3 + 1] = __fdiv_rn(__fadd_rn(__fdiv_rn(ny, den), cbuf[8][i]), fh);
+                P.cand_scyx[o * 3 + 2] = __fdiv_rn(__fadd_rn(__fdiv_rn(nx, den), cbuf[9][i]), fw);
+            }
+        }
+        __syncwarp();
+        buf_n = 0;
+    };
+
+    // consume pyramid row c (slot PN = c % 3): the response row of image row r0-3+c enters slot PN; output row y = r0+c-4 is the
+    // response row of slot PM (one step old), its neighbours above / below are slots PO / PN
+    auto step = [&](auto PC, const int c) {
+        constexpr int PN = decltype(PC)::value, PM = (PN + 2) % 3, PO = (PN + 1) % 3;
+        asm volatile("cp.async.wait_group %0;" ::"n"(WPD - 1) : "memory");
+        __syncwarp();
+        const float (*row)[WROWLEN] = ring[c % WRING];
+        const int yy = r0 - 3 + c;
+        const bool in = col_in && c >= 2 && yy >= 0 && yy < h;
+#pragma unroll
+        for (int d = 0; d < 5; d++) {
+            const float L = row[d][lane], C = row[d][lane + 1], R = row[d][lane + 2];
+            pc[d][PN] = C;
+            ph[d][PN] = __fsub_rn(__fmul_rn(0.5f, L), __fmul_rn(0.5f, R));
+            pg[d][PN] = __fadd_rn(__fsub_rn(L, __fmul_rn(2.0f, C)), R);
+            // hessian_regs with t = slot PO, m = slot PM, b = this row
+            const float gyy = __fadd_rn(__fsub_rn(pc[d][PO], __fmul_rn(2.0f, pc[d][PM])), C);
+            const float gxy = __fsub_rn(__fmul_rn(0.5f, ph[d][PO]), __fmul_rn(0.5f, ph[d][PN]));
+            const float det = __fsub_rn(__fmul_rn(pg[d][PM], gyy), __fmul_rn(gxy, gxy));
+            float r = fmaxf(__fsub_rn(__fmul_rn(fabsf(det), s4[d]), th), 0.0f);
+            r = in ? r : 0.f;
+            float l = __shfl_up_sync(0xffffffffu, r, 1), rr = __shfl_down_sync(0xffffffffu, r, 1);
+            l = (lane == 0) ? 0.f : l;
+            rr = (lane == 31) ? 0.f : rr;
+            rs[d][PN] = r;
+            rmx[d][PN] = fmaxf(fmaxf(l, r), rr);
+            hs[d][PN] = (l + r) + rr;
+            hx[d][PN] = fmaf(1.5f, rr, fmaf(0.5f, r, -0.5f * l));   // x offsets [-0.5, 0.5, 1.5] (Q2)
+        }
+        if (c >= 4) {
+            const int y = r0 + c - 4;
+            float n1 = 0.f, n2 = 0.f, n3 = 0.f;
+            if (col_ok && y >= P.mr_border && y < h - P.mr_border) {
+                float M[5];
+#pragma unroll
+                for (int d = 0; d < 5; d++) M[d] = fmaxf(fmaxf(rmx[d][PO], rmx[d][PM]), rmx[d][PN]);
+                const float x1 = rs[1][PM], x2 = rs[2][PM], x3 = rs[3][PM];
+                n1 = (__fadd_rn(__fsub_rn(x1, fmaxf(fmaxf(M[0], M[1]), M[2])), 1e-5f) > 0.f) ? x1 : 0.f;   // NMS3d, HandCraftedModules.py:220
+                n2 = (__fadd_rn(__fsub_rn(x2, fmaxf(fmaxf(M[1], M[2]), M[3])), 1e-5f) > 0.f) ? x2 : 0.f;
+                n3 = (__fadd_rn(__fsub_rn(x3, fmaxf(fmaxf(M[2], M[3]), M[4])), 1e-5f) > 0.f) ? x3 : 0.f;
+            }
+            const unsigned m1 = __ballot_sync(0xffffffffu, n1 != 0.f), m2 = __ballot_sync(0xffffffffu, n2 != 0.f), m3 = __ballot_sync(0xffffffffu, n3 != 0.f);
+            if (m1 | m2 | m3) {
+                const int row_total = __popc(m1) + __popc(m2) + __popc(m3);
+                if (buf_n + row_total > WCBUF) flush();
+                if ((n1 != 0.f) || (n2 != 0.f) || (n3 != 0.f)) {
+                    var[0] += n1 > 0.f; var[7] += n1 != 0.f;
+#pragma unroll
+                    for (int a1 = 0; a1 < 2; a1++) {
+                        const uint8_t om1 = a1 ? om_after(0, n1) : (uint8_t)0;
+                        const float v2 = masked(n2, om1);
+                        var[1 + a1] += v2 > 0.f; var[8 + a1] += v2 != 0.f;
+#pragma unroll
+                        for (int a2 = 0; a2 < 2; a2++) {
+                            const uint8_t om2 = a2 ? om_after(om1, v2) : om1;
+                            const float v3 = masked(n3, om2);
+                            var[3 + a1 * 2 + a2] += v3 > 0.f; var[10 + a1 * 2 + a2] += v3 != 0.f;
+                        }
+                    }
+                    // soft-argmax sums (HandCraftedModules.py:266-290) from the horizontal sums of the three rows; the divisions wait for the flush
+                    const unsigned lt = (1u << lane) - 1u;
+                    const float nn[3] = {n1, n2, n3};
+                    const int pos[3] = {buf_n + __popc(m1 & lt), buf_n + __popc(m1) + __popc(m2 & lt), buf_n + __popc(m1) + __popc(m2) + __popc(m3 & lt)};
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        if (nn[q] == 0.f) continue;
+                        float ns = 0.f, ny = 0.f, nx = 0.f, den = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            const float S = (hs[q + d][PO] + hs[q + d][PM]) + hs[q + d][PN];
+                            ns = fmaf(sc[q + d], S, ns);
+                            ny += fmaf(1.5f, hs[q + d][PN], fmaf(0.5f, hs[q + d][PM], -0.5f * hs[q + d][PO]));
+                            nx += (hx[q + d][PO] + hx[q + d][PM]) + hx[q + d][PN];
+                            den += S;
+                        }
+                        const int dst = pos[q];
+                        cbuf[0][dst] = nn[q];
+                        cbuf[1][dst] = n1;
+                        cbuf[2][dst] = n2;
+                        cbuf[3][dst] = __uint_as_float(((uint32_t)(oi * 3 + q) << SEQ_PIX_BITS) | (uint32_t)(y * w + gx));
+                        cbuf[4][dst] = ns;
+                        cbuf[5][dst] = ny;
+                        cbuf[6][dst] = nx;
+                        cbuf[7][dst] = __fadd_rn(den, 1e-8f);
+                        cbuf[8][dst] = (float)y;
+                        cbuf[9][dst] = (float)gx;
+                    }
+                }
+                buf_n += row_total;
+            }
+        }
+        __syncwarp();            // every lane has read ring row c before slot (c+WPD) % WRING is refilled
+        issue_row(c + WPD);
+    };
+
+#pragma unroll 1
+    for (int c = 0; c < WPD; c++) issue_row(c);
+#pragma unroll 1
+    for (int c = 0; c < n_rows; c += 3) {
+        step(IC<0>{}, c);
+        if (c + 1 < n_rows) step(IC<1>{}, c + 1);
+        if (c + 2 < n_rows) step(IC<2>{}, c + 2);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    flush();
+#pragma unroll
+    for (int i = 0; i < 14; i++) {
+        int v = var[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&P.variants[((size_t)b * P.n_oct + oi) * NVAR + i], v);
+    }
+}
+
 // Picks the hypothesis branch the counters select, fills level_pos / level_emit, and turns every candidate's raw NMS value
 // into the reference's masked response (or invalidates it: slot 31 is never accepted).
 __global__ void resolve_kernel(const int* __restrict__ variants, int n_oct, int cand_cap, const int* __restrict__ cand_count,
@@ -1000,8 +1228,14 @@ int ag_detect(const ag_pyramid_plan_t* p, const float* d_pyr, float th, int mr_b
                 units += O.strips_x * O.bands_y;
             }
             Wp.total_units = units;
-            detect_warp_kernel<<<dim3(cdiv(units, WNT / 32), p->B), WNT, 0, st>>>(Wp);
-            AG_CHECK_LAUNCH("detect_warp_kernel");
+            static const bool use_v1 = getenv("AG_DETECT_WARP_V1") != nullptr;     // A/B switch: the first register formulation
+            if (use_v1) {
+                detect_warp_kernel<<<dim3(cdiv(units, WNT / 32), p->B), WNT, 0, st>>>(Wp);
+                AG_CHECK_LAUNCH("detect_warp_kernel");
+            } else {
+                detect_rows_kernel<<<dim3(cdiv(units, WNT / 32), p->B), WNT, 0, st>>>(Wp);
+                AG_CHECK_LAUNCH("detect_rows_kernel");
+            }
             resolve_kernel<<<dim3(8, p->B), 256, 0, st>>>(ws->d_variants, p->n_octaves, ws->cand_cap, ws->d_cand_count, ws->d_cand_val, ws->d_cand_aux,
                                                            ws->d_cand_seq, ws->d_level_pos, ws->d_level_emit);
             AG_CHECK_LAUNCH("resolve_kernel");
