@@ -678,9 +678,13 @@ __device__ __forceinline__ void cp_async4_off_if(uint32_t dst, const float* src,
                  : "memory");
 }
 
+static_assert(WROWS <= 255, "8-bit per-lane hypothesis counters");
 constexpr int RCB = 10;   // staged candidate record: val, n1, n2, seq, ns, ny, nx, den, y, x
 
-__global__ void __launch_bounds__(WNT, 3) detect_rows_kernel(const WarpParams P) {
+#ifndef AG_DETROWS_MINB
+#define AG_DETROWS_MINB 3   // 168 registers (4 B of spills), three CTAs per SM: 0.43 - 0.44 ms; 2 CTAs at 202 registers 0.47 - 0.49; 4 CTAs at 128 registers 0.59
+#endif
+__global__ void __launch_bounds__(WNT, AG_DETROWS_MINB) detect_rows_kernel(const WarpParams P) {
     __shared__ float s_ring[WNT / 32][WRING][5][WROWLEN];
     __shared__ float s_cbuf[WNT / 32][RCB][WCBUF];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -692,10 +696,12 @@ __global__ void __launch_bounds__(WNT, 3) detect_rows_kernel(const WarpParams P)
         if (u >= P.oct[i].unit_base) oi = i;
     u -= P.oct[oi].unit_base;
     // octave constants into registers (dynamically indexed kernel parameters are constant-bank loads at every use otherwise)
-    const float* lvl[5];
-    float s4[5], sc[5];
+    // (the five level pointers become one pointer + 32-bit element offsets: the levels of an octave lie in one pyramid allocation)
+    const float* const lvl0 = P.oct[oi].lvl[0];
+    int loff[5];
+    float s4[5];
 #pragma unroll
-    for (int d = 0; d < 5; d++) { lvl[d] = P.oct[oi].lvl[d]; s4[d] = P.oct[oi].s4[d]; sc[d] = P.oct[oi].sc[d]; }
+    for (int d = 0; d < 5; d++) { loff[d] = (int)(P.oct[oi].lvl[d] - lvl0); s4[d] = P.oct[oi].s4[d]; }
     const int h = P.oct[oi].h, w = P.oct[oi].w, strips_x = P.oct[oi].strips_x;
     const float th = P.th;
     const int b = blockIdx.y;
@@ -706,7 +712,7 @@ __global__ void __launch_bounds__(WNT, 3) detect_rows_kernel(const WarpParams P)
     const int cx = clampi(gx, 0, w - 1);
     const bool halo_lane = lane == 0 || lane == 31;
     const int hdelta = (lane == 0 ? clampi(gx - 1, 0, w - 1) : clampi(gx + 1, 0, w - 1)) - cx;   // extra column of the halo lanes
-    const int base_off = b * h * w + cx;                 // < 2^31: a level of the whole batch is indexed with int elsewhere too
+    const int base_off = b * h * w + cx;                 // element offsets inside one pyramid allocation fit an int (ag_detect checks)
     const bool border_ok = (P.mr_border < w) && (P.mr_border < h);
     const bool col_ok = lane >= 1 && lane <= WCOLS && col_in && border_ok && gx >= P.mr_border && gx < w - P.mr_border;
     const int rows_out = min(WROWS, h - r0);
@@ -720,11 +726,11 @@ __global__ void __launch_bounds__(WNT, 3) detect_rows_kernel(const WarpParams P)
             const int cy = clampi(r0 - 2 + c, 0, h - 1);
             const int off = base_off + cy * w;
             const uint32_t so = (uint32_t)((c % WRING) * (5 * WROWLEN * 4));
-            cp_async4_off<0 * WROWLEN * 4>(sdst + so, lvl[0] + off); cp_async4_off_if<0 * WROWLEN * 4>(sdst_h + so, lvl[0] + off + hdelta, halo_lane);
-            cp_async4_off<1 * WROWLEN * 4>(sdst + so, lvl[1] + off); cp_async4_off_if<1 * WROWLEN * 4>(sdst_h + so, lvl[1] + off + hdelta, halo_lane);
-            cp_async4_off<2 * WROWLEN * 4>(sdst + so, lvl[2] + off); cp_async4_off_if<2 * WROWLEN * 4>(sdst_h + so, lvl[2] + off + hdelta, halo_lane);
-            cp_async4_off<3 * WROWLEN * 4>(sdst + so, lvl[3] + off); cp_async4_off_if<3 * WROWLEN * 4>(sdst_h + so, lvl[3] + off + hdelta, halo_lane);
-            cp_async4_off<4 * WROWLEN * 4>(sdst + so, lvl[4] + off); cp_async4_off_if<4 * WROWLEN * 4>(sdst_h + so, lvl[4] + off + hdelta, halo_lane);
+            cp_async4_off<0 * WROWLEN * 4>(sdst + so, lvl0 + (loff[0] + off)); cp_async4_off_if<0 * WROWLEN * 4>(sdst_h + so, lvl0 + (loff[0] + off + hdelta), halo_lane);
+            cp_async4_off<1 * WROWLEN * 4>(sdst + so, lvl0 + (loff[1] + off)); cp_async4_off_if<1 * WROWLEN * 4>(sdst_h + so, lvl0 + (loff[1] + off + hdelta), halo_lane);
+            cp_async4_off<2 * WROWLEN * 4>(sdst + so, lvl0 + (loff[2] + off)); cp_async4_off_if<2 * WROWLEN * 4>(sdst_h + so, lvl0 + (loff[2] + off + hdelta), halo_lane);
+            cp_async4_off<3 * WROWLEN * 4>(sdst + so, lvl0 + (loff[3] + off)); cp_async4_off_if<3 * WROWLEN * 4>(sdst_h + so, lvl0 + (loff[3] + off + hdelta), halo_lane);
+            cp_async4_off<4 * WROWLEN * 4>(sdst + so, lvl0 + (loff[4] + off)); cp_async4_off_if<4 * WROWLEN * 4>(sdst_h + so, lvl0 + (loff[4] + off + hdelta), halo_lane);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -736,9 +742,9 @@ __global__ void __launch_bounds__(WNT, 3) detect_rows_kernel(const WarpParams P)
     for (int d = 0; d < 5; d++)
 #pragma unroll
         for (int q = 0; q < 3; q++) { pc[d][q] = 0.f; ph[d][q] = 0.f; pg[d][q] = 0.f; rs[d][q] = 0.f; rmx[d][q] = 0.f; hs[d][q] = 0.f; hx[d][q] = 0.f; }
-    int var[14];
-#pragma unroll
-    for (int i = 0; i < 14; i++) var[i] = 0;
+    // hypothesis counters of this lane, four 8-bit counters per register (a lane counts at most once per row and counter: <= WROWS = 32)
+    unsigned varp[4] = {0u, 0u, 0u, 0u};
+    auto bump = [&](int i, bool cond) { varp[i >> 2] += cond ? (1u << ((i & 3) * 8)) : 0u; };
     const float min_size = (float)min(h, w);
     const float fh = (float)h, fw = (float)w;
 
@@ -814,17 +820,17 @@ __global__ void __launch_bounds__(WNT, 3) detect_rows_kernel(const WarpParams P)
                 const int row_total = __popc(m1) + __popc(m2) + __popc(m3);
                 if (buf_n + row_total > WCBUF) flush();
                 if ((n1 != 0.f) || (n2 != 0.f) || (n3 != 0.f)) {
-                    var[0] += n1 > 0.f; var[7] += n1 != 0.f;
+                    bump(0, n1 > 0.f); bump(7, n1 != 0.f);
 #pragma unroll
                     for (int a1 = 0; a1 < 2; a1++) {
                         const uint8_t om1 = a1 ? om_after(0, n1) : (uint8_t)0;
                         const float v2 = masked(n2, om1);
-                        var[1 + a1] += v2 > 0.f; var[8 + a1] += v2 != 0.f;
+                        bump(1 + a1, v2 > 0.f); bump(8 + a1, v2 != 0.f);
 #pragma unroll
                         for (int a2 = 0; a2 < 2; a2++) {
                             const uint8_t om2 = a2 ? om_after(om1, v2) : om1;
                             const float v3 = masked(n3, om2);
-                            var[3 + a1 * 2 + a2] += v3 > 0.f; var[10 + a1 * 2 + a2] += v3 != 0.f;
+                            bump(3 + a1 * 2 + a2, v3 > 0.f); bump(10 + a1 * 2 + a2, v3 != 0.f);
                         }
                     }
                     // soft-argmax sums (HandCraftedModules.py:266-290) from the horizontal sums of the three rows; the divisions wait for the flush
@@ -838,7 +844,7 @@ __global__ void __launch_bounds__(WNT, 3) detect_rows_kernel(const WarpParams P)
 #pragma unroll
                         for (int d = 0; d < 3; d++) {
                             const float S = (hs[q + d][PO] + hs[q + d][PM]) + hs[q + d][PN];
-                            ns = fmaf(sc[q + d], S, ns);
+                            ns = fmaf(P.oct[oi].sc[q + d], S, ns);
                             ny += fmaf(1.5f, hs[q + d][PN], fmaf(0.5f, hs[q + d][PM], -0.5f * hs[q + d][PO]));
                             nx += (hx[q + d][PO] + hx[q + d][PM]) + hx[q + d][PN];
                             den += S;
@@ -875,7 +881,7 @@ __global__ void __launch_bounds__(WNT, 3) detect_rows_kernel(const WarpParams P)
     flush();
 #pragma unroll
     for (int i = 0; i < 14; i++) {
-        int v = var[i];
+        int v = (int)((varp[i >> 2] >> ((i & 3) * 8)) & 0xFFu);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0 && v) atomicAdd(&P.variants[((size_t)b * P.n_oct + oi) * NVAR + i], v);
@@ -1229,7 +1235,14 @@ int ag_detect(const ag_pyramid_plan_t* p, const float* d_pyr, float th, int mr_b
             }
             Wp.total_units = units;
             static const bool use_v1 = getenv("AG_DETECT_WARP_V1") != nullptr;     // A/B switch: the first register formulation
-            if (use_v1) {
+            // detect_rows_kernel addresses an octave's levels with 32-bit element offsets from its first level
+            bool fits32 = true;
+            for (int o = 0; o < p->n_octaves; o++) {
+                long long lo = 0, hi = 0;
+                for (int d = 0; d < 5; d++) { const long long off = Wp.oct[o].lvl[d] - Wp.oct[o].lvl[0]; lo = off < lo ? off : lo; hi = off > hi ? off : hi; }
+                if (lo < -(1ll << 30) || hi + (long long)p->B * p->h[o] * p->w[o] >= (1ll << 31) - 64) fits32 = false;
+            }
+            if (use_v1 || !fits32) {
                 detect_warp_kernel<<<dim3(cdiv(units, WNT / 32), p->B), WNT, 0, st>>>(Wp);
                 AG_CHECK_LAUNCH("detect_warp_kernel");
             } else {

@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(NT) blur_kernel(const float* __restrict__ in, 
     // interior tiles: same values in the same places as the clamped fill below, so the arithmetic does not change
     const bool wide = (w & 3) == 0 && x0 - R4 >= 0 && x0 - R4 + G::IW <= w && (reinterpret_cast<size_t>(img) & 15) == 0;
 #ifndef AG_BLUR_LDG_FILL
-    // ... and tiles that need no row clamp either take the window as IH bulk copies (one 16-byte-aligned row segment each, issued by
-    // warp 0, completion counted on one mbarrier): no thread spends issue slots or registers on the fill
+    // ... and tiles that need no row clamp either take the window as IH bulk copies (one 16-byte-aligned row segment each, completion
+    // counted on one mbarrier): no thread spends issue slots or registers on moving the data
     __shared__ __align__(8) unsigned long long s_bar;
     const bool bulk = wide && y0 - R >= 0 && y0 - R + G::IH <= h;    // block-uniform
     if (bulk) {
@@ -122,15 +122,18 @@ __global__ void __launch_bounds__(NT) blur_kernel(const float* __restrict__ in, 
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(G::IH * G::IW * 4)) : "memory");
         }
         __syncthreads();
-        if (threadIdx.x < 32) {
+        if ((threadIdx.x & 31) == 0) {     // one lane per warp issues every (NT/32)-th row: the bulk-copy instruction is warp-uniform, 8 issuers shorten the queue
             const float* src = img + (size_t)(y0 - R) * w + (x0 - R4);
-            for (int ly = threadIdx.x; ly < G::IH; ly += 32)
+            for (int ly = threadIdx.x >> 5; ly < G::IH; ly += NT / 32)
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                                  (uint32_t)__cvta_generic_to_shared(s_in + ly * G::IW)),
                              "l"(src + (size_t)ly * w), "r"((uint32_t)(G::IW * 4)), "r"(bar)
                              : "memory");
         }
-        asm volatile("{\n .reg .pred P;\n W_%=:\n mbarrier.try_wait.parity.shared::cta.b64 P, [%0], 0;\n @P bra D_%=;\n bra W_%=;\n D_%=:\n}\n" ::"r"(bar) : "memory");
+        // warp 0 alone polls the mbarrier (256 polling threads spent 18 % of the kernel's issue slots in the try_wait loop); the others
+        // wait in the block barrier below, which orders their reads after warp 0's acquire
+        if (threadIdx.x < 32)
+            asm volatile("{\n .reg .pred P;\n W_%=:\n mbarrier.try_wait.parity.shared::cta.b64 P, [%0], 0;\n @P bra D_%=;\n bra W_%=;\n D_%=:\n}\n" ::"r"(bar) : "memory");
     } else
 #endif
     // 128-bit loads (the scalar fill was 30 % of this kernel's stall samples)

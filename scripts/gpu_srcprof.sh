@@ -8,7 +8,6 @@ cap() { name=$1; shift
   ncu -i gpurun_out/$name.ncu-rep --page raw --csv > gpurun_out/$name.csv 2>/dev/null
   rm -f gpurun_out/$name.ncu-rep
 }
-cap src_blur -k "regex:blur_kernel" -s 76 -c 1 $B
-cap src_detect -k "regex:detect_warp_kernel" -s 3 -c 1 $B
-cap src_select -k "regex:select_kernel" -s 3 -c 1 $B
+cap src_blur -k "regex:blur_kernel" -s 75 -c 1 $B
+cap src_detect -k "regex:detect_rows_kernel" -s 3 -c 1 $B
 ls -la gpurun_out | head -30
