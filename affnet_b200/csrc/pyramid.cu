@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
+
 #include "common.cuh"
 #include "pyramid_fused.cuh"
 
@@ -96,9 +98,10 @@ struct BlurGeom {
 
 template <int R>
 __global__ void __launch_bounds__(NT) blur_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                   float* __restrict__ dec, int h, int w, BlurTaps taps) {
+                                                   float* __restrict__ dec, int h, int w, BlurTaps taps,
+                                                   const __grid_constant__ CUtensorMap tmap, int use_tmap) {
     using G = BlurGeom<R>;
-    extern __shared__ __align__(16) float smem_f[];
+    extern __shared__ __align__(128) float smem_f[];
     float* s_in = smem_f;                       // [IH][IW]; column c holds image column x0 - R4 + c, R4 = R rounded up to 4
     float* s_mid = smem_f + G::IH * G::IW;      // [IH][TW]
     constexpr int R4 = (R + 3) / 4 * 4;
@@ -122,7 +125,14 @@ __global__ void __launch_bounds__(NT) blur_kernel(const float* __restrict__ in, 
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(G::IH * G::IW * 4)) : "memory");
         }
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) {     // one lane per warp issues every (NT/32)-th row: the bulk-copy instruction is warp-uniform, 8 issuers shorten the queue
+        if (use_tmap) {
+            // the whole window is ONE box of the level's tensor map [B][h][w] (TMA tile mode: IW x IH x 1 floats land densely = s_in's layout)
+            if (threadIdx.x == 0)
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(s_in)),
+                             "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - R4), "r"(y0 - R), "r"(b), "r"(bar)
+                             : "memory");
+        } else if ((threadIdx.x & 31) == 0) {     // one lane per warp issues every (NT/32)-th row: the bulk-copy instruction is warp-uniform, 8 issuers shorten the queue
             const float* src = img + (size_t)(y0 - R) * w + (x0 - R4);
             for (int ly = threadIdx.x >> 5; ly < G::IH; ly += NT / 32)
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -218,18 +228,54 @@ __global__ void __launch_bounds__(NT) blur_kernel(const float* __restrict__ in, 
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link against libcuda); NULL when the driver has none
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {
+    static TmapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        if (getenv("AG_BLUR_NO_TMA") == nullptr) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+                fn = reinterpret_cast<TmapEncodeFn>(p);
+            else
+                cudaGetLastError();
+        }
+    }
+    return fn;
+}
+
+// tensor map of one pyramid level [B][h][w] fp32 with a box of iw x ih x 1 elements; false when the level cannot be described (then the
+// kernel's row-by-row bulk copies are used)
+static bool make_level_tmap(CUtensorMap* m, const float* base, int B, int h, int w, int iw, int ih) {
+    TmapEncodeFn enc = tmap_encoder();
+    if (enc == nullptr || (w & 3) != 0 || (reinterpret_cast<size_t>(base) & 15) != 0 || iw > 256 || ih > 256) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4};        // bytes, dimensions 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)iw, (cuuint32_t)ih, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch_blur(const float* in, float* out, float* dec, int B, int h, int w, double sigma, cudaStream_t st) {
     BlurTaps taps;
     int rc = make_taps(sigma, &taps);
     if (rc != AG_OK) return rc;
     dim3 grid(cdiv(w, TW), cdiv(h, TH), B), block(NT);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
     switch (taps.r) {
 #define AG_BLUR_CASE(R)                                                                                                   \
     case R: {                                                                                                             \
         static SmemAttrOnce attr_once;                                                                                    \
         rc = attr_once.ensure(blur_kernel<R>, BlurGeom<R>::SMEM, "blur smem attr");                                       \
         if (rc != AG_OK) return rc;                                                                                       \
-        blur_kernel<R><<<grid, block, BlurGeom<R>::SMEM, st>>>(in, out, dec, h, w, taps);                                  \
+        const int use_tmap = make_level_tmap(&tmap, in, B, h, w, BlurGeom<R>::IW, BlurGeom<R>::IH) ? 1 : 0;                 \
+        blur_kernel<R><<<grid, block, BlurGeom<R>::SMEM, st>>>(in, out, dec, h, w, taps, tmap, use_tmap);                  \
     } break;
         AG_BLUR_CASE(1) AG_BLUR_CASE(2) AG_BLUR_CASE(3) AG_BLUR_CASE(4) AG_BLUR_CASE(5) AG_BLUR_CASE(6)
         AG_BLUR_CASE(7) AG_BLUR_CASE(8) AG_BLUR_CASE(9) AG_BLUR_CASE(10) AG_BLUR_CASE(11) AG_BLUR_CASE(12)
