@@ -1,11 +1,12 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py -m gpu -q -x > gpurun_out/pytest_pyr.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_pyr.log
-for v in tma notma tma notma; do
-  if [ $v = notma ]; then export AG_BLUR_NO_TMA=1; else unset AG_BLUR_NO_TMA; fi
-  timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err; echo "bench rc=$?"
-  python - <<PY
-import json
-d=json.load(open("gpurun_out/bench_$v.json"))
-print("$v", round(d["value"],1), "Mpix/s", round(d["ms_per_step"],3), "ms/step", {k:round(v,3) for k,v in d["roofline"]["stages_ms"].items() if "detect" in k or "blur" in k or "select" in k})
-PY
-done
+mkdir -p gpurun_out
+bash scripts/gpu_ab.sh base _hint base _hint
+B="python bench.py --steps 1 --warmup 3 --batch 16 --no-cpu-baseline --no-graph --no-extras"
+cap() { name=$1; shift
+  ncu --set full --import-source on --clock-control none --kernel-name-base demangled -o gpurun_out/$name -f "$@" > gpurun_out/ncu_$name.log 2>&1
+  ncu -i gpurun_out/$name.ncu-rep --page source --csv > gpurun_out/$name.source.csv 2>/dev/null
+  rm -f gpurun_out/$name.ncu-rep
+}
+cap src_first -k "regex:tcx_first_kernel" -s 9 -c 1 $B
+cap src_conv -k "regex:tcx_conv_kernel" -s 37 -c 1 $B
+ls -la gpurun_out/src_*
