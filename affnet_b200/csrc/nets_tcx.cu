@@ -161,6 +161,13 @@ size_t tcx_act_bytes(int n) { return (size_t)(n + 1) * 65536; }
 // ---- trunks -------------------------------------------------------------------------------------------------------------------------
 // AffNet / OriNet (same shapes, own weights): features as fp16 hi + lo planes in the head-GEMM layout.  upto: stop after conv layer
 // `upto` (2..6; for the debug decode), 6 = whole trunk.
+// epilogue warps of AffNet / OriNet layers 3 and 4 (4 | 8)
+#ifndef AG_AFF_EW3
+#define AG_AFF_EW3 4
+#endif
+#ifndef AG_AFF_EW4
+#define AG_AFF_EW4 8   // layer 4 waited for its 4-warp epilogue 23 % of the time: 0.72 -> 0.61 ms (AffNet), 0.48 -> 0.41 (OriNet); layer 3 is HBM bound (no change)
+#endif
 int tcx_trunk_affori(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, void* feat,
                      cudaStream_t st, int upto) {
     using namespace tcx;
@@ -169,9 +176,9 @@ int tcx_trunk_affori(const ag_net* net, const tc::FirstSrc& src0, int n, int gro
     int rc;
     if ((rc = launch_first<16, 16, 1, 1, 1>(bufB, net->d_wx[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src))) return rc;
     if (upto <= 2) return AG_OK;
-    if ((rc = launch_conv<16, 32, 32, 2, 1, 3, L_S1_16, 1, 1, 1, 4>(bufB, bufA, net->d_wx[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
+    if ((rc = launch_conv<16, 32, 32, 2, 1, 3, L_S1_16, 1, 1, 1, AG_AFF_EW3>(bufB, bufA, net->d_wx[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
     if (upto <= 3) return AG_OK;
-    if ((rc = launch_conv<32, 32, 16, 1, 1, 4, L_S2_8P, 1, 1, 1, 4>(bufA, bufB, net->d_wx[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
+    if ((rc = launch_conv<32, 32, 16, 1, 1, 4, L_S2_8P, 1, 1, 1, AG_AFF_EW4>(bufA, bufB, net->d_wx[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
     if (upto <= 4) return AG_OK;
     if ((rc = launch_conv<32, 64, 16, 2, 1, 2, L_S1_8P, 1, 1, 1, 8>(bufB, bufA, net->d_wx[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
     if (upto <= 5) return AG_OK;

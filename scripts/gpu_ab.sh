@@ -7,6 +7,7 @@ for v in "$@"; do
   python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_ab$v.json"))
-print("[$v]", round(d["value"],1), "Mpix/s", round(d["ms_per_step"],3), "ms/step", {k:round(v,3) for k,v in d["roofline"]["stages_ms"].items() if "detect" in k or "blur" in k or "select" in k})
+print("[$v]", round(d["value"],1), "Mpix/s", round(d["ms_per_step"],3), "ms/step", {k:round(v,3) for k,v in d["roofline"]["stages_ms"].items() if "detect" in k or "blur" in k or "select" in k or "tcx" in k})
+print("   convs:", [round(v,3) for k,v in d["roofline"]["launches_ms"] if k.startswith("tcx_conv")])
 PY
 done
