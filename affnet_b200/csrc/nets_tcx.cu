@@ -162,6 +162,12 @@ size_t tcx_act_bytes(int n) { return (size_t)(n + 1) * 65536; }
 // AffNet / OriNet (same shapes, own weights): features as fp16 hi + lo planes in the head-GEMM layout.  upto: stop after conv layer
 // `upto` (2..6; for the debug decode), 6 = whole trunk.
 // epilogue warps of AffNet / OriNet layers 3 and 4 (4 | 8)
+#ifndef AG_HARD_EW4
+#define AG_HARD_EW4 16   // HardNet layer 4 (N = 192, two accumulator buffers): 16 epilogue warps = 2 tile sets x 2 column halves, 0.56 -> 0.49 ms
+#endif
+#ifndef AG_AFF_EW6
+#define AG_AFF_EW6 8
+#endif
 #ifndef AG_AFF_EW3
 #define AG_AFF_EW3 4
 #endif
@@ -182,7 +188,7 @@ int tcx_trunk_affori(const ag_net* net, const tc::FirstSrc& src0, int n, int gro
     if (upto <= 4) return AG_OK;
     if ((rc = launch_conv<32, 64, 16, 2, 1, 2, L_S1_8P, 1, 1, 1, 8>(bufB, bufA, net->d_wx[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
     if (upto <= 5) return AG_OK;
-    return launch_conv<64, 64, 8, 1, 1, 2, L_HEAD, 1, 1, 1, 8>(bufA, feat, net->d_wx[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st);
+    return launch_conv<64, 64, 8, 1, 1, 2, L_HEAD, 1, 1, 1, AG_AFF_EW6>(bufA, feat, net->d_wx[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st);
 }
 
 template <int BF>
@@ -197,7 +203,7 @@ static int trunk_hardnet_t(const ag_net* net, const tc::FirstSrc& src0, int n, i
     if (upto <= 2) return AG_OK;
     if ((rc = launch_conv<32, 64, 32, 2, 1, 2, L_S1_16, 0, AG_HARD_SW3, 0, 8, BF>(bufB, bufA, wx[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
     if (upto <= 3) return AG_OK;
-    if ((rc = launch_conv<64, 64, 16, 1, 1, 2, L_S2_8P, 0, AG_HARD_SW4, 0, 8, BF>(bufA, bufB, wx[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
+    if ((rc = launch_conv<64, 64, 16, 1, 1, 2, L_S2_8P, 0, AG_HARD_SW4, 0, AG_HARD_EW4, BF>(bufA, bufB, wx[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
     if (upto <= 4) return AG_OK;
     if ((rc = launch_conv<64, 128, 16, 2, 2, 2, L_S1_8P, 0, 0, 0, 8, BF>(bufB, bufA, wx[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
     if (upto <= 5) return AG_OK;

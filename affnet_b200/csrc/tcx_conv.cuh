@@ -125,7 +125,7 @@ struct XArgs {
     const int* count;     // valid patches per image (NULL: all)
 };
 
-// SA: input hi/lo planes; SW: weight hi/lo copies; OSA: write hi/lo planes.  OUT: layout of the output buffer.  EW: epilogue warps (4 | 8).
+// SA: input hi/lo planes; SW: weight hi/lo copies; OSA: write hi/lo planes.  OUT: layout of the output buffer.  EW: epilogue warps (4 | 8 | 16).
 template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW>
 struct XCfg {
     using In = XIn<H, STRIDE>;
@@ -145,7 +145,9 @@ struct XCfg {
     static constexpr int NR1 = (1 + SW) * 3 * NT;                              // stride 1: [hi: dx0 dx1 dx2][lo: dx0 dx1 dx2]
     static constexpr int NRO = (1 + SW) * 2 * NT, NRE = (1 + SW) * NT;         // stride 2: odd-x plane [hi: dx0 dx2][lo: ...], even-x plane [hi: dx1][lo: dx1]
     static_assert(CIN % 16 == 0 && NT % 16 == 0 && ACCW <= 256 && NACC >= 2, "UMMA shape");
-    static_assert(EW == 4 || EW == 8, "epilogue warps");
+    static_assert(EW == 4 || EW == 8 || EW == 16, "epilogue warps");
+    static constexpr int CS = (EW == 16) ? 2 : 1;     // EW = 16: two tile sets x two column halves (an accumulator is read by 8 warps)
+    static_assert((NT / 16) % CS == 0, "column split");
     static_assert(2 * STAGES + 2 * NACC + 1 <= 60, "barrier area");
     static_assert(SMEM <= 232448, "shared memory budget");
     static_assert(GS < 16384, "leading-byte offset field");
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
     if (threadIdx.x < NT) s_bias[threadIdx.x] = a.bias[split * NT + threadIdx.x];
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int i = 0; i < NACC; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < NACC; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * Cfg::CS); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -297,9 +299,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
         XP_STORE(a.prof_id, 0);
     } else {
         // ===== epilogue: EW / 4 sets of four warps (TMEM lane quadrant = warp % 4), set k takes tiles k, k + NSETS, ... =====
-        constexpr int NSETS = EW / 4;
+        constexpr int CS = Cfg::CS, NSETS = EW / 4 / CS;    // tile sets; each made of CS column parts of four warps
         const int q = warp & 3;
-        const int set = warp >> 2;
+        const int set = (warp >> 2) / CS, cpart = (warp >> 2) % CS;
         const int r = q * 32 + lane;                         // tile row of this thread
         int tcnt = 0;
         RP_DECL;
@@ -330,13 +332,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
                     lo_off = (size_t)(COUT / 8) * layout_slots(OUT) * 16;
                 }
 #pragma unroll 1
-                for (int c0 = 0; c0 < NT; c0 += 16) {
+                for (int c0 = cpart * 16; c0 < NT; c0 += 16 * CS) {
                     uint32_t r0[16], r1[16], r2[16];
                     tmem_ld16(taddr + (uint32_t)c0, r0);                   // stride 1: dx0 | stride 2: odd plane dx0
                     tmem_ld16(taddr + (uint32_t)(NT + c0), r1);            // stride 1: dx1 | stride 2: odd plane dx2
                     tmem_ld16(taddr + (uint32_t)(2 * NT + c0), r2);        // stride 1: dx2 | stride 2: even plane dx1
                     tmem_ld_wait();
-                    if (c0 + 16 >= NT) {   // last column chunk read: release the accumulator buffer
+                    if (c0 + 16 * CS >= NT) {   // this warp's last column chunk read: release the accumulator buffer (4 CS arrivals)
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty[ab]);
