@@ -219,7 +219,7 @@ def emit(real_stdout, line):
 
 
 TC_FAMILY = ("tc_first2_kernel", "tc_conv_kernel", "tc_conv_pair_kernel", "tc_head_kernel", "tc_headx_kernel", "tcx_first_kernel", "tcx_conv_kernel")
-STENCIL = ("blur_kernel", "octave_kernel", "pyramid_tail_kernel", "detect_level_kernel", "detect_fused_kernel", "detect_warp_kernel", "resolve_kernel")
+STENCIL = ("blur_kernel", "octave_kernel", "pyramid_tail_kernel", "detect_level_kernel", "detect_fused_kernel", "detect_warp_kernel", "detect_rows_kernel", "resolve_kernel")
 
 
 class Workload:

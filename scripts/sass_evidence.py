@@ -12,13 +12,13 @@ import sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 PAT = collections.OrderedDict([
     ("UTC*MMA (tcgen05.mma)", r"\bUTC[A-Z]*MMA\b"), ("LDTM (tcgen05.ld)", r"\bLDTM\b"), ("UTCBAR (tcgen05.commit)", r"\bUTCBAR\b"),
-    ("UTCATOM* (tcgen05.alloc/dealloc)", r"\bUTCATOM[A-Z.]*"), ("UBLKCP (cp.async.bulk)", r"\bUBLKCP\b"), ("SYNCS (mbarrier)", r"\bSYNCS\b"),
+    ("UTCATOM* (tcgen05.alloc/dealloc)", r"\bUTCATOM[A-Z.]*"), ("UBLKCP (cp.async.bulk)", r"\bUBLKCP\b"), ("UTMALDG (TMA tensor map)", r"\bUTMALDG\b"), ("SYNCS (mbarrier)", r"\bSYNCS\b"),
     ("UCGABAR (cluster barrier)", r"\bUCGABAR[A-Z_.]*"), ("LDGSTS (cp.async)", r"\bLDGSTS\b"), ("ELECT", r"\bELECT\b"),
 ])
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     lib = os.path.join(ROOT, "affnet_b200", "lib", "libaffnet_b200.so")
     txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
     demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()
@@ -41,7 +41,7 @@ def main():
     for k, c in kernels.items():
         name = re.sub(r"^(void )?(ag::)?(tcx?::|pf::)?", "", demangle(k))
         name = re.sub(r"\(.*$", "", name)
-        if not any(c[p] for p in list(PAT)[:5]) and not name.startswith(("detect_warp", "blur", "select_kernel", "octave")):
+        if not any(c[p] for p in list(PAT)[:6]) and not name.startswith(("detect_warp", "detect_rows", "blur", "select_kernel", "octave")):
             continue
         md.append("| `%s` | %d | " % (name, c["_n"]) + " | ".join(str(c[p]) for p in PAT) + " |")
     open(os.path.join(ROOT, "profiles", tag + "_sass_evidence.md"), "w").write("\n".join(md) + "\n")
