@@ -41,11 +41,11 @@ static int ensure_smem_attr(const void* func, int bytes, bool* configured, const
     return rc;
 }
 
-template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW, int BF = 0>
+template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW, int BF = 0, int MC = 0>
 static int launch_conv(const void* in, void* out, const __half* w, const float* b, float inv_scale, int n, int group, const int* count, cudaStream_t st) {
     constexpr int prof_id = (H == 32) ? 2 : (H == 16 ? (STRIDE == 1 ? 3 : 4) : 5);
     using Cfg = XCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW>;
-    auto kern = tcx_conv_kernel<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW, BF>;
+    auto kern = tcx_conv_kernel<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW, BF, MC>;
     static bool configured[64] = {};   // per device (the attribute is per device)
     int rc = ensure_smem_attr((const void*)kern, (int)Cfg::SMEM, configured, "tcx_conv smem attr");
     if (rc != AG_OK) return rc;
@@ -55,7 +55,18 @@ static int launch_conv(const void* in, void* out, const __half* w, const float* 
     int gx = num_sms() / NSPLIT;
     if (gx > units) gx = units;
     if (gx < 1) gx = 1;
-    kern<<<dim3(gx, NSPLIT), Cfg::THREADS, Cfg::SMEM, st>>>(a);
+    if (MC) {   // the two channel-split CTAs of a unit as one thread-block cluster (1 x 2)
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(gx, NSPLIT); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        rc = check_cuda(cudaLaunchKernelEx(&cfg, kern, a), "tcx_conv cluster launch");
+        if (rc != AG_OK) return rc;
+    } else
+        kern<<<dim3(gx, NSPLIT), Cfg::THREADS, Cfg::SMEM, st>>>(a);
     AG_CHECK_LAUNCH("tcx_conv_kernel");
     return AG_OK;
 }
@@ -162,6 +173,13 @@ size_t tcx_act_bytes(int n) { return (size_t)(n + 1) * 65536; }
 // AffNet / OriNet (same shapes, own weights): features as fp16 hi + lo planes in the head-GEMM layout.  upto: stop after conv layer
 // `upto` (2..6; for the debug decode), 6 = whole trunk.
 // epilogue warps of AffNet / OriNet layers 3 and 4 (4 | 8)
+// cluster-multicast input of HardNet's channel-split layers: layer 5 0.38 -> 0.35 ms, layer 6 unchanged (kept off)
+#ifndef AG_HARD_MC5
+#define AG_HARD_MC5 1
+#endif
+#ifndef AG_HARD_MC6
+#define AG_HARD_MC6 0
+#endif
 #ifndef AG_HARD_EW4
 #define AG_HARD_EW4 16   // HardNet layer 4 (N = 192, two accumulator buffers): 16 epilogue warps = 2 tile sets x 2 column halves, 0.56 -> 0.49 ms
 #endif
@@ -205,9 +223,9 @@ static int trunk_hardnet_t(const ag_net* net, const tc::FirstSrc& src0, int n, i
     if (upto <= 3) return AG_OK;
     if ((rc = launch_conv<64, 64, 16, 1, 1, 2, L_S2_8P, 0, AG_HARD_SW4, 0, AG_HARD_EW4, BF>(bufA, bufB, wx[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
     if (upto <= 4) return AG_OK;
-    if ((rc = launch_conv<64, 128, 16, 2, 2, 2, L_S1_8P, 0, 0, 0, 8, BF>(bufB, bufA, wx[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
+    if ((rc = launch_conv<64, 128, 16, 2, 2, 2, L_S1_8P, 0, 0, 0, 8, BF, AG_HARD_MC5>(bufB, bufA, wx[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
     if (upto <= 5) return AG_OK;
-    return launch_conv<128, 128, 8, 1, 2, 2, L_HEAD, 0, 0, 0, 8, BF>(bufA, headbuf, wx[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st);
+    return launch_conv<128, 128, 8, 1, 2, 2, L_HEAD, 0, 0, 0, 8, BF, AG_HARD_MC6>(bufA, headbuf, wx[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st);
 }
 
 int tcx_trunk_hardnet(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, void* headbuf,
