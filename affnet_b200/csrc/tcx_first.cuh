@@ -47,7 +47,10 @@ struct XFirstCfg {
     static constexpr size_t SMEM = 1024 + (size_t)W_BYTES + IN_BYTES + P_BYTES + W1_BYTES + 2 * SX * 4 + 256;
     static constexpr int OUT_G = (COUT / 8) * (1 + OSA);
     static constexpr size_t UNIT_OUT_BYTES = (size_t)OUT_G * 1024 * 16;
-    static constexpr int NSET = (C1 >= 32) ? 3 : 2;            // layer-2 epilogue sets of four warps (HardNet's 32-channel epilogue is its critical role: three sets)
+#ifndef AG_FIRST_NSET16
+#define AG_FIRST_NSET16 2   // three sets measured slower for the 16-channel nets (4.05 -> 4.28 ms per step over the three first kernels)
+#endif
+    static constexpr int NSET = (C1 >= 32) ? 3 : AG_FIRST_NSET16;            // layer-2 epilogue sets of four warps (HardNet's 32-channel epilogue is its critical role: three sets)
     static constexpr int W_L2 = 8, W_L1 = W_L2 + 4 * NSET, W_MMA = W_L1 + 4;   // first warp of each role (producers: warps 0-7)
     static constexpr int THREADS = (W_MMA + 1) * 32;
     static_assert(C1 % 16 == 0 && NT % 16 == 0 && NACC >= 2 && ACCW <= 256, "shape");
