@@ -93,12 +93,18 @@ __global__ void tcx_decode_kernel(const __half* __restrict__ buf, int layout, in
     const size_t total = (size_t)n * C * H * H;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int x = (int)(i % H), y = (int)((i / H) % H), c = (int)((i / ((size_t)H * H)) % C), pi = (int)(i / ((size_t)H * H * C));
-        const int slots = layout_slots(layout), groups = (C / 8) * (1 + osa);
+        const int slots = layout_slots(layout);
+        const size_t unit_halfs = (size_t)(C / 8) * slots * 8 * (osa == 1 ? 2 : 1) + (osa == 2 ? (size_t)(C / 8) * slots * 4 : 0);
         const int unit = layout_pair(layout) ? (pi >> 1) : pi;
         const int slot = layout_slot(layout, y, x, pi & 1);
-        const __half* ub = buf + (size_t)unit * groups * slots * 8;
+        const __half* ub = buf + (size_t)unit * unit_halfs;
         float v = __half2float(ub[((size_t)(c / 8) * slots + slot) * 8 + (c & 7)]);
-        if (osa) v += __half2float(ub[((size_t)(C / 8 + c / 8) * slots + slot) * 8 + (c & 7)]);
+        if (osa == 1) v += __half2float(ub[((size_t)(C / 8 + c / 8) * slots + slot) * 8 + (c & 7)]);
+        if (osa == 2) {   // byte residual planes behind the hi planes
+            const unsigned char* lb = reinterpret_cast<const unsigned char*>(ub) + (size_t)(C / 8) * slots * 16;
+            const unsigned short bits = (unsigned short)(lb[((size_t)(c / 8) * slots + slot) * 8 + (c & 7)] << 8);
+            v += __half2float(__ushort_as_half(bits));
+        }
         out[i] = v;
     }
 }
@@ -186,27 +192,44 @@ size_t tcx_act_bytes(int n) { return (size_t)(n + 1) * 65536; }
 #ifndef AG_AFF_EW6
 #define AG_AFF_EW6 8
 #endif
+// Residual planes of layer 2's output (the largest activation, read by the HBM-bound layer 3) as bytes (1) or fp16 (0).  Measured
+// (tests/test_gpu_tcx.py, bench A/B): AffNet's A stays at 4.5e-6 of the oracle and layer 3 goes from 0.80 to 0.69 ms per step; the same
+// in front of layer 5 made that layer SLOWER (0.37 -> 0.41 ms: the expansion sits between a two-stage ring and the MMAs), so it is not
+// used there.  OriNet's angle error grows from 3e-5 to 1.2e-4 rad with byte planes (its atan2 amplifies): off by default for OriNet.
+#ifndef AG_AFF_LO8
+#define AG_AFF_LO8 1
+#endif
+#ifndef AG_ORI_LO8
+#define AG_ORI_LO8 0
+#endif
+static inline int tcx_lox(const ag_net* net) { return ((net->kind == AG_NET_AFFNET) ? AG_AFF_LO8 : AG_ORI_LO8) ? 2 : 1; }
 #ifndef AG_AFF_EW3
 #define AG_AFF_EW3 4
 #endif
 #ifndef AG_AFF_EW4
 #define AG_AFF_EW4 8   // layer 4 waited for its 4-warp epilogue 23 % of the time: 0.72 -> 0.61 ms (AffNet), 0.48 -> 0.41 (OriNet); layer 3 is HBM bound (no change)
 #endif
-int tcx_trunk_affori(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, void* feat,
-                     cudaStream_t st, int upto) {
+template <int LOX>
+static int trunk_affori_t(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, void* feat,
+                          cudaStream_t st, int upto) {
     using namespace tcx;
     tc::FirstSrc src = src0;
     src.w1 = net->d_w1; src.b1 = net->d_b[0]; src.w1_inv = net->w_inv_scale[0]; src.w1_scale = 1.0f / net->w_inv_scale[0];
     int rc;
-    if ((rc = launch_first<16, 16, 1, 1, 1>(bufB, net->d_wx[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src))) return rc;
+    if ((rc = launch_first<16, 16, 1, 1, LOX>(bufB, net->d_wx[1], net->d_b[1], net->w_inv_scale[1], n, group, count, st, src))) return rc;
     if (upto <= 2) return AG_OK;
-    if ((rc = launch_conv<16, 32, 32, 2, 1, 3, L_S1_16, 1, 1, 1, AG_AFF_EW3>(bufB, bufA, net->d_wx[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
+    if ((rc = launch_conv<16, 32, 32, 2, 1, 3, L_S1_16, LOX, 1, 1, AG_AFF_EW3>(bufB, bufA, net->d_wx[2], net->d_b[2], net->w_inv_scale[2], n, group, count, st))) return rc;
     if (upto <= 3) return AG_OK;
     if ((rc = launch_conv<32, 32, 16, 1, 1, 4, L_S2_8P, 1, 1, 1, AG_AFF_EW4>(bufA, bufB, net->d_wx[3], net->d_b[3], net->w_inv_scale[3], n, group, count, st))) return rc;
     if (upto <= 4) return AG_OK;
     if ((rc = launch_conv<32, 64, 16, 2, 1, 2, L_S1_8P, 1, 1, 1, 8>(bufB, bufA, net->d_wx[4], net->d_b[4], net->w_inv_scale[4], n, group, count, st))) return rc;
     if (upto <= 5) return AG_OK;
     return launch_conv<64, 64, 8, 1, 1, 2, L_HEAD, 1, 1, 1, AG_AFF_EW6>(bufA, feat, net->d_wx[5], net->d_b[5], net->w_inv_scale[5], n, group, count, st);
+}
+int tcx_trunk_affori(const ag_net* net, const tc::FirstSrc& src0, int n, int group, const int* count, void* bufA, void* bufB, void* feat,
+                     cudaStream_t st, int upto) {
+    return tcx_lox(net) == 2 ? trunk_affori_t<2>(net, src0, n, group, count, bufA, bufB, feat, st, upto)
+                             : trunk_affori_t<1>(net, src0, n, group, count, bufA, bufB, feat, st, upto);
 }
 
 template <int BF>
@@ -260,7 +283,9 @@ int ag_debug_tcx_layer(const ag_net_t* net, const float* d_patches, int n, int u
     const int Cb = hard ? 32 : 16;
     const int C = upto == 2 ? Cb : (upto <= 4 ? 2 * Cb : 4 * Cb);
     const void* buf = (upto == 2 || upto == 4) ? base + act : base;
-    tcx::tcx_decode_kernel<<<296, 256, 0, st>>>((const __half*)buf, lay, C, hard ? 0 : 1, H, n, d_out);
+    // the planes layer 2 writes carry byte residuals when the net uses them (tcx_lox)
+    const int osa = hard ? 0 : (upto == 2 ? tcx_lox(net) : 1);
+    tcx::tcx_decode_kernel<<<296, 256, 0, st>>>((const __half*)buf, lay, C, osa, H, n, d_out);
     AG_CHECK_LAUNCH("tcx_decode_kernel");
     return AG_OK;
 }

@@ -101,6 +101,14 @@ __device__ __forceinline__ void split_pack8(const float* v, uint4& hi, uint4& lo
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// Byte residual planes (SA / OSA = 2): the fp16 residual rounded to its high byte (= e5m2).  Emulation (scripts/emu_residual_bits.py):
+// AffNet's output moves by 5e-6 when the residual of an activation keeps 2 mantissa bits (budget 5e-5), so the planes that cross HBM
+// in front of the bandwidth-bound stride-2 layers are stored at half the size and expanded in shared memory by the consumer.
+__device__ __forceinline__ uint2 pack_lo8(const uint4& lo) {
+    const uint32_t t0 = lo.x + 0x00800080u, t1 = lo.y + 0x00800080u, t2 = lo.z + 0x00800080u, t3 = lo.w + 0x00800080u;   // round the magnitude to 8 bits
+    return make_uint2(__byte_perm(t0, t1, 0x7531), __byte_perm(t2, t3, 0x7531));
+}
+
 // slots per channel group and unit of an HBM activation layout, and patches per unit
 __host__ __device__ constexpr int layout_slots(int lay) { return lay == L_S2_16 ? 1024 : lay == L_S1_16 ? 256 : lay == L_S2_8P ? 512 : 128; }
 __host__ __device__ constexpr int layout_pair(int lay) { return (lay == L_S2_8P || lay == L_S1_8P) ? 1 : 0; }
@@ -140,22 +148,25 @@ struct XArgs {
     const int* count;     // valid patches per image (NULL: all)
 };
 
-// SA: input hi/lo planes; SW: weight hi/lo copies; OSA: write hi/lo planes.  OUT: layout of the output buffer.  EW: epilogue warps (4 | 8 | 16).
+// SA: input hi/lo planes (2: the lo planes arrive as bytes); SW: weight hi/lo copies; OSA: write hi/lo planes (2: lo as bytes).  OUT: layout of the output buffer.  EW: epilogue warps (4 | 8 | 16).
 template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW>
 struct XCfg {
     using In = XIn<H, STRIDE>;
     static constexpr int KC = CIN / 8, NT = COUT / NSPLIT, HOUT = In::HOUT;
-    static constexpr int G = KC * (1 + SA);                                   // channel groups of one unit
+    static constexpr int HAS_LO = SA ? 1 : 0, LO8 = (SA == 2) ? 1 : 0;      // SA = 2: the residual planes arrive as bytes
+    static constexpr int G = KC * (1 + HAS_LO);                               // channel groups of one unit (in shared memory)
     static constexpr int GS = STAGES * In::SLOT_STAGE + (STRIDE == 1 ? In::RW : 0);   // slots per channel group in shared memory
     static constexpr int ACCW = 3 * NT;                                        // accumulator columns of one tile
     static constexpr int NACC = (512 / ACCW) < 4 ? (512 / ACCW) : 4;
     static constexpr uint32_t W_BYTES = 9u * CIN * NT * 2u * (1 + SW);         // per split
     static constexpr uint32_t IN_BYTES = (uint32_t)G * GS * 16u;               // all stages
-    static constexpr uint32_t UNIT_IN_BYTES = (uint32_t)G * In::NPLANES * In::DATA * 16u;   // one unit in HBM
-    static constexpr int THREADS = 64 + 32 * EW;
+    static constexpr uint32_t HI_IN_BYTES = (uint32_t)KC * In::NPLANES * In::DATA * 16u;
+    static constexpr uint32_t UNIT_IN_BYTES = HI_IN_BYTES + (SA == 1 ? HI_IN_BYTES : SA == 2 ? HI_IN_BYTES / 2 : 0u);   // one unit in HBM
+    static constexpr int NCONV = 4;                                            // LO8: converter warps (one alone was the new critical path: 32 dependent steps per unit)
+    static constexpr int THREADS = 64 + 32 * EW + 32 * NCONV * LO8;
     static constexpr size_t SMEM = 1024 + (size_t)W_BYTES + IN_BYTES;
-    static constexpr int OUT_G = (COUT / 8) * (1 + OSA);
-    static constexpr size_t UNIT_OUT_BYTES = (OUT == L_HEAD) ? 0 : (size_t)OUT_G * layout_slots(OUT) * 16;
+    static constexpr size_t HI_OUT_BYTES = (size_t)(COUT / 8) * layout_slots(OUT) * 16;
+    static constexpr size_t UNIT_OUT_BYTES = (OUT == L_HEAD) ? 0 : HI_OUT_BYTES + (OSA == 1 ? HI_OUT_BYTES : OSA == 2 ? HI_OUT_BYTES / 2 : 0);
     // weight rows per K group of one (dy, k step) block
     static constexpr int NR1 = (1 + SW) * 3 * NT;                              // stride 1: [hi: dx0 dx1 dx2][lo: dx0 dx1 dx2]
     static constexpr int NRO = (1 + SW) * 2 * NT, NRE = (1 + SW) * NT;         // stride 2: odd-x plane [hi: dx0 dx2][lo: ...], even-x plane [hi: dx1][lo: dx1]
@@ -163,7 +174,9 @@ struct XCfg {
     static_assert(EW == 4 || EW == 8 || EW == 16, "epilogue warps");
     static constexpr int CS = (EW == 16) ? 2 : 1;     // EW = 16: two tile sets x two column halves (an accumulator is read by 8 warps)
     static_assert((NT / 16) % CS == 0, "column split");
-    static_assert(2 * STAGES + 2 * NACC + 1 <= 60, "barrier area");
+    static_assert(3 * STAGES + 2 * NACC + 1 <= 60, "barrier area");
+    static_assert(!LO8 || (STRIDE == 2 && In::DATA % 64 == 0), "byte residual planes: stride-2 consumers");
+    static_assert(OSA != 2 || OUT == L_S2_16 || OUT == L_S2_8P, "byte residual planes are written for stride-2 consumers");
     static_assert(SMEM <= 232448, "shared memory budget");
     static_assert(GS < 16384, "leading-byte offset field");
     static_assert(OUT == L_HEAD || layout_pair(OUT) || !In::PAIR, "a pair layer writes pair layouts or the head operand");
@@ -172,7 +185,7 @@ struct XCfg {
 // MC = 1 (NSPLIT = 2 only): the two CTAs of a unit form a thread-block cluster (1 x 2); each loader fetches half of the unit's planes and
 // multicasts them to both, so the input crosses the L2 -> SM fabric once instead of twice (HardNet layer 5 waited for its input 40 % of the time).
 template <int CIN, int COUT, int H, int STRIDE, int NSPLIT, int STAGES, int OUT, int SA, int SW, int OSA, int EW, int BF = 0, int MC = 0>
-__global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a) {
+__global__ void __launch_bounds__(64 + 32 * EW + (SA == 2 ? 128 : 0), 1) tcx_conv_kernel(const XArgs a) {
     static_assert(MC == 0 || NSPLIT == 2, "multicast pairs the two channel-split CTAs");
     using Cfg = XCfg<CIN, COUT, H, STRIDE, NSPLIT, STAGES, OUT, SA, SW, OSA, EW>;
     using In = typename Cfg::In;
@@ -184,7 +197,10 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
     uint64_t* tfull = empty + STAGES;                      // [NACC]
     uint64_t* tempty = tfull + NACC;                       // [NACC]
     uint64_t* wbar = tempty + NACC;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    uint64_t* cfull = wbar + 1;                            // [STAGES] byte planes of the stage expanded (LO8)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfull + STAGES);
+    constexpr int LO8 = Cfg::LO8;
+    static_assert(!(BF && (SA == 2 || OSA == 2)), "byte residual planes are fp16");
     float* s_bias = reinterpret_cast<float*>(smem + 512);  // [NT]
     unsigned char* sW = smem + 1024;
     unsigned char* sIn = sW + Cfg::W_BYTES;
@@ -195,7 +211,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
 
     if (threadIdx.x < NT) s_bias[threadIdx.x] = a.bias[split * NT + threadIdx.x];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1 + MC); }   // MC: both CTAs' MMAs must have read a stage
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1 + MC); mbar_init(&cfull[s], Cfg::NCONV); }   // MC: both CTAs' MMAs must have read a stage
         for (int i = 0; i < NACC; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * Cfg::CS); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -235,7 +251,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
                     for (int pl = 0; pl < In::NPLANES; pl++) {
                         unsigned char* dst = sIn + ((size_t)g * GS + (size_t)s * In::SLOT_STAGE + (size_t)pl * In::PLANE + RW) * 16;
                         const unsigned char* srcp = gsrc + ((size_t)g * In::NPLANES + pl) * In::DATA * 16;
-                        if (MC) { if (((g * In::NPLANES + pl) & 1) == split) bulk_g2s_mc(dst, srcp, In::DATA * 16u, &full[s], (uint16_t)3); }
+                        if (LO8 && g >= KC) {   // byte plane: into the upper half of the fp16 plane's place, expanded there by the converter warp
+                            bulk_g2s(dst + In::DATA * 8, gsrc + Cfg::HI_IN_BYTES + ((size_t)(g - KC) * In::NPLANES + pl) * In::DATA * 8, In::DATA * 8u, &full[s]);
+                        } else if (MC) { if (((g * In::NPLANES + pl) & 1) == split) bulk_g2s_mc(dst, srcp, In::DATA * 16u, &full[s], (uint16_t)3); }
                         else bulk_g2s(dst, srcp, In::DATA * 16u, &full[s]);
                     }
                 it++;
@@ -261,7 +279,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             if (!uvalid(u)) continue;
             const int s = it % STAGES;
-            RP_WAIT(0, mbar_wait(&full[s], (it / STAGES) & 1));
+            RP_WAIT(0, mbar_wait(LO8 ? &cfull[s] : &full[s], (it / STAGES) & 1));
             tc_fence_after();
             const uint32_t st_base = in_base + (uint32_t)(s * In::SLOT_STAGE);
 #pragma unroll 1
@@ -322,6 +340,38 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
             it++;
         }
         XP_STORE(a.prof_id, 0);
+    } else if (LO8 && warp >= EW + 2) {
+        // ===== converters (NCONV warps, regions dealt round robin): byte residual planes -> fp16 in place (byte j of a slot pair becomes the
+        // fp16 with that high byte).  The bytes sit in the upper half of the plane's place; a warp reads a whole region (16 bytes per lane and
+        // step) into registers before it writes the expanded 32 bytes per lane and step, so nothing is overwritten before it is read =====
+        constexpr int NST = In::DATA / 64;                    // steps of 32 lanes x 16 bytes per region
+        const int cw = warp - (EW + 2);
+        int it = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            if (!uvalid(u)) continue;
+            const int s = it % STAGES;
+            mbar_wait(&full[s], (it / STAGES) & 1);
+#pragma unroll 1
+            for (int r = cw; r < KC * In::NPLANES; r += Cfg::NCONV) {
+                const int g = KC + r / In::NPLANES, pl = r % In::NPLANES;
+                unsigned char* region = sIn + ((size_t)g * GS + (size_t)s * In::SLOT_STAGE + (size_t)pl * In::PLANE + RW) * 16;
+                uint4 b[NST];
+#pragma unroll
+                for (int k = 0; k < NST; k++) b[k] = *reinterpret_cast<const uint4*>(region + In::DATA * 8 + (k * 32 + lane) * 16);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < NST; k++) {
+                    *reinterpret_cast<uint4*>(region + (k * 32 + lane) * 32) =
+                        make_uint4(__byte_perm(b[k].x, 0u, 0x1404), __byte_perm(b[k].x, 0u, 0x3424), __byte_perm(b[k].y, 0u, 0x1404), __byte_perm(b[k].y, 0u, 0x3424));
+                    *reinterpret_cast<uint4*>(region + (k * 32 + lane) * 32 + 16) =
+                        make_uint4(__byte_perm(b[k].z, 0u, 0x1404), __byte_perm(b[k].z, 0u, 0x3424), __byte_perm(b[k].w, 0u, 0x1404), __byte_perm(b[k].w, 0u, 0x3424));
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cfull[s]);
+            it++;
+        }
     } else {
         // ===== epilogue: EW / 4 sets of four warps (TMEM lane quadrant = warp % 4), set k takes tiles k, k + NSETS, ... =====
         constexpr int CS = Cfg::CS, NSETS = EW / 4 / CS;    // tile sets; each made of CS column parts of four warps
@@ -347,6 +397,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACCW);
                 // output position
                 unsigned char* obase = nullptr;
+                unsigned char* obase8 = nullptr;     // OSA = 2: byte residual planes behind the hi planes
                 size_t lo_off = 0;
                 if (OUT == L_HEAD) {
                     obase = reinterpret_cast<unsigned char*>(a.out) + (((size_t)(pi >> 7) * (HOUT * HOUT * COUT / 8) + (size_t)(y * HOUT + x) * (COUT / 8)) * 128 + (pi & 127)) * 16;
@@ -355,6 +406,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
                     const int ou = layout_pair(OUT) ? (pi >> 1) : pi;
                     obase = reinterpret_cast<unsigned char*>(a.out) + (size_t)ou * Cfg::UNIT_OUT_BYTES + (size_t)layout_slot(OUT, y, x, pi & 1) * 16;
                     lo_off = (size_t)(COUT / 8) * layout_slots(OUT) * 16;
+                    obase8 = reinterpret_cast<unsigned char*>(a.out) + (size_t)ou * Cfg::UNIT_OUT_BYTES + Cfg::HI_OUT_BYTES + (size_t)layout_slot(OUT, y, x, pi & 1) * 8;
                 }
 #pragma unroll 1
                 for (int c0 = cpart * 16; c0 < NT; c0 += 16 * CS) {
@@ -390,7 +442,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) tcx_conv_kernel(const XArgs a
                             uint4 hi, lo;
                             split_pack8<OSA, BF>(v + g * 8, hi, lo);
                             *reinterpret_cast<uint4*>(obase + goff) = hi;
-                            if (OSA) *reinterpret_cast<uint4*>(obase + lo_off + goff) = lo;
+                            if (OSA == 1) *reinterpret_cast<uint4*>(obase + lo_off + goff) = lo;
+                            if (OSA == 2) *reinterpret_cast<uint2*>(obase8 + (size_t)cg * layout_slots(OUT) * 8) = pack_lo8(lo);
                         }
                     }
                 }

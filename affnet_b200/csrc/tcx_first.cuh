@@ -45,8 +45,8 @@ struct XFirstCfg {
     static constexpr uint32_t W1_BYTES = 2u * 2u * C1 * 16;    // [K chunk 0|1][hi rows | lo rows][8]
     static constexpr uint32_t P_BYTES = 2u * 2u * NPIXP * 16;   // [half][hi | lo][NPIXP]: the halves are built and consumed alternately
     static constexpr size_t SMEM = 1024 + (size_t)W_BYTES + IN_BYTES + P_BYTES + W1_BYTES + 2 * SX * 4 + 256;
-    static constexpr int OUT_G = (COUT / 8) * (1 + OSA);
-    static constexpr size_t UNIT_OUT_BYTES = (size_t)OUT_G * 1024 * 16;
+    static constexpr size_t HI_OUT_BYTES = (size_t)(COUT / 8) * 1024 * 16;
+    static constexpr size_t UNIT_OUT_BYTES = HI_OUT_BYTES + (OSA == 1 ? HI_OUT_BYTES : OSA == 2 ? HI_OUT_BYTES / 2 : 0);   // OSA = 2: byte residual planes
 #ifndef AG_FIRST_NSET16
 #define AG_FIRST_NSET16 2   // three sets measured slower for the 16-channel nets (4.05 -> 4.28 ms per step over the three first kernels)
 #endif
@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(XFirstCfg<C1, COUT, SA, SW, OSA>::THREADS, 1) 
                         uint4 hi, lo;
                         split_pack8<OSA, BF>(v + g * 8, hi, lo);
                         *reinterpret_cast<uint4*>(obase + goff) = hi;
-                        if (OSA) *reinterpret_cast<uint4*>(obase + (size_t)(COUT / 8) * 1024 * 16 + goff) = lo;
+                        if (OSA == 1) *reinterpret_cast<uint4*>(obase + (size_t)(COUT / 8) * 1024 * 16 + goff) = lo;
+                        if (OSA == 2) *reinterpret_cast<uint2*>(outp + Cfg::HI_OUT_BYTES + ((size_t)(c0 / 8 + g) * 1024 + layout_slot(L_S2_16, y, x, 0)) * 8) = pack_lo8(lo);
                     }
                 }
             }
