@@ -57,9 +57,8 @@ def patches():
 @pytest.mark.parametrize("kind", ["affnet", "orinet", "hardnet"])
 def test_tcx_layers_vs_oracle(L, nets, kind):
     """Layers 2..5 stage by stage (layer 1 is fused into the same kernel as layer 2).  AffNet / OriNet carry hi + lo planes: 2e-5 of
-    the layer's largest activation where the residual plane is fp16 (3e-5 behind a byte plane), 8e-5 where it is stored as a byte (AffNet
-    after layer 2: fp16 + e5m2 of the rest = 2^-14 of the value at worst); HardNet single fp16 planes: 2e-3 (one
-    fp16 rounding of the stored value plus operand rounding)."""
+    the layer's largest activation; HardNet single fp16 planes: 2e-3 (one fp16 rounding of the stored value plus operand rounding).
+    (A build with -DAG_AFF_LO8=1 stores AffNet's layer-2 residual plane as bytes: measured 1.9e-5 / 1.6e-5 / 2.8e-5 / 1.5e-5 on layers 2..5.)"""
     net = dict(zip(("affnet", "orinet", "hardnet"), nets))[kind]
     cfg = O.HARDNET_CFG if kind == "hardnet" else O.AFFNET_CFG
     P = patches()
@@ -69,8 +68,8 @@ def test_tcx_layers_vs_oracle(L, nets, kind):
     ws_bytes = lib.ag_net_workspace_bytes(net.KIND, n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
     Pd = P.to(DEV).contiguous()
+    tol = 2e-3 if kind == "hardnet" else 2e-5
     for upto in (2, 3, 4, 5):
-        tol = 2e-3 if kind == "hardnet" else (8e-5 if upto == 2 else 3e-5)
         r = ref[upto - 1]
         out = torch.full(r.shape, float("nan"), device=DEV)
         L.check(lib.ag_debug_tcx_layer(net.handle(), L.ptr(Pd), n, upto, L.ptr(out), L.ptr(ws), ws_bytes, L.stream_ptr()))
