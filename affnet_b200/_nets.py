@@ -60,8 +60,9 @@ class _NativeNet(nn.Module):
         return self._handle
 
     def set_engine(self, engine):
-        """engine: L.ENGINE_SIMT (exact fp32 CUDA cores), L.ENGINE_TC (tcgen05, default), L.ENGINE_TC_EXACT (AffNet / OriNet: fp32
-        heads on top of the residual-plane trunk) or L.ENGINE_TC_FAST (AffNet without activation residuals); see include/affnet_b200.h."""
+        """engine: L.ENGINE_TC2 (second-generation tcgen05 engine, default), L.ENGINE_TC2_BF16 (HardNet with bf16 operands), L.ENGINE_SIMT
+        (exact fp32 CUDA cores), L.ENGINE_TC / L.ENGINE_TC_EXACT / L.ENGINE_TC_FAST (first-generation tcgen05 engine and its variants); see
+        include/affnet_b200.h."""
         self._engine = engine
         if self._handle is not None:
             L.check(L.lib().ag_net_set_engine(self._handle, engine))
@@ -77,10 +78,13 @@ class _NativeNet(nn.Module):
                 L.lib().ag_net_destroy(self._handle)
             except Exception:
                 pass
-            self._handle = None
+            object.__setattr__(self, "_handle", None)     # not nn.Module.__setattr__: at interpreter shutdown torch's globals may be gone
 
     def __del__(self):
-        self._release()
+        try:
+            self._release()
+        except Exception:
+            pass
 
     def _check_input(self, x):
         L.require_cuda(x, "input patches")
