@@ -163,13 +163,14 @@ typedef struct ag_net ag_net_t;
 int ag_net_create(int kind, const float* h_blob, size_t n_floats, ag_net_t** out);
 void ag_net_destroy(ag_net_t* net);
 size_t ag_net_blob_floats(int kind);
-/* Compute engine: 0 = exact fp32 SIMT (needs materialised patches); 1 = tcgen05 tensor cores (default for all three nets): fp16
+/* Compute engine: 0 = exact fp32 SIMT (needs materialised patches); 1 = first-generation tcgen05 engine (round 1; one MMA per tap): fp16
  * operands, fp32 accumulation in TMEM, all six conv layers and the 8x8 heads as MMAs; AffNet and OriNet carry fp16 residual
  * planes of weights AND activations in every layer (fp32-grade: A 1e-5, angle 3e-5 rad - OriNet's atan2 amplifies an error of
  * AffNet's A about 15x, so the 1e-3 LAF contract needs A to 5e-5), HardNet plain fp16 operands (descriptors 6e-4);
  * 2 = as 1 with fp32 FMA-chain heads (A 2e-6, angle 3e-6 rad; AffNet/OriNet only); 3 = AffNet with the weight residual only
  * (A 2e-4; for A/B timing, AffNet only);
- * 4 = second-generation tcgen05 engine (same operand precision as 1, plus fp16 residuals of HardNet's layer 2-3 weights): 128-pixel
+ * 4 = second-generation tcgen05 engine, THE DEFAULT for all three nets (same operand precision as 1, plus fp16 residuals of HardNet's
+ * layer 2-3 weights: descriptors 4e-4): 128-pixel
  * row tiles without x padding, the three taps of a kernel row stacked along N of one MMA, x shifts by warp shuffles in the epilogue;
  * 5 = engine 4 with bf16 operands (HardNet only; BASELINE.json configs[4] "bf16 HardNet tensor-core path"; descriptors ~4e-3). */
 int ag_net_set_engine(ag_net_t* net, int engine);
