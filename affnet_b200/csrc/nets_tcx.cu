@@ -196,7 +196,8 @@ size_t tcx_act_bytes(int n) { return (size_t)(n + 1) * 65536; }
 // (tests/test_gpu_tcx.py, bench A/B): with byte planes AffNet's A stays at 4.5e-6 of the oracle and layer 3 goes from 0.80 to 0.69 ms per
 // step (the same in front of layer 5 made that layer slower, 0.37 -> 0.41 ms: not wired).  OFF by default: the application test with the
 // hand-crafted orientation (test_graf_1_to_6_application_counts[hcori]) then has one keypoint of 2996 whose frame differs from the
-// oracle's by more than its near-tie accounting allows, and that was not run to ground in this round.  OriNet's angle error grows from
+// oracle's by more than its near-tie accounting allows (a pixel on a histogram-bin boundary; the accounting would
+// have to cover that case before the switch can be on).  OriNet's angle error grows from
 // 3e-5 to 1.2e-4 rad with byte planes (its atan2 amplifies): off for OriNet as well.
 #ifndef AG_AFF_LO8
 #define AG_AFF_LO8 0
