@@ -92,3 +92,32 @@ def synthetic_image(H, W, seed):
     x = F.conv2d(F.pad(x, (0, 0, k // 2, k // 2), "replicate"), k1.view(1, 1, k, 1))
     x = (x - x.min()) / (x.max() - x.min()) * 255.0
     return x.contiguous()
+
+
+def orientation_boundary_shares(patches, tol_bins=1e-4, num_bins=36):
+    """Hand-crafted orientation (HandCraftedModules.py:168-190) accumulates only the LOWER-bin weight (1 - frac) * magnitude of every pixel,
+    so a pixel whose gradient orientation lies on a bin boundary moves its whole weight between two bins under an arbitrarily small change of
+    the patch.  For patches [n,1,PS,PS] returns (margin [n], share [n]): the relative margin between the two best smoothed bins, and the
+    largest weight - relative to the best bin - among the pixels within `tol_bins` of a boundary (0 if none).  share > margin means: an
+    epsilon perturbation can legitimately change the arg-max bin although the two best bins are not tied."""
+    import math
+
+    import torch.nn.functional as F
+
+    import affnet_oracle as O
+    PS = patches.size(2)
+    xp = F.pad(patches, (1, 1, 0, 0), "replicate")
+    gx = 0.5 * xp[:, :, :, :-2] - 0.5 * xp[:, :, :, 2:]
+    yp = F.pad(patches, (0, 0, 1, 1), "replicate")
+    gy = 0.5 * yp[:, :, :-2, :] - 0.5 * yp[:, :, 2:, :]
+    gk = 10.0 * torch.from_numpy(O.circular_gauss_kernel(PS).astype(np.float32))
+    mag = torch.sqrt(gx * gx + gy * gy + 1e-10) * gk
+    o_big = float(num_bins) * (torch.atan2(gy, gx) + math.pi) / (2.0 * math.pi)
+    frac = o_big - torch.floor(o_big)
+    dist = torch.minimum(frac, 1.0 - frac).flatten(1)
+    sm = O.orientation_hist_bins(patches, num_bins)
+    top = sm.topk(2, dim=1).values
+    margin = (top[:, 0] - top[:, 1]) / top[:, 0]
+    w = (mag.flatten(1) / float(PS * PS)) / top[:, :1]
+    share = torch.where(dist < tol_bins, w, torch.zeros_like(w)).amax(dim=1)
+    return margin, share

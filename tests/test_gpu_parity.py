@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import affnet_oracle as O
-from helpers import TOL, gold, gray_from_rgb, laf_rel_errors, load_weights, match_keypoints, parity_report
+from helpers import TOL, gold, gray_from_rgb, laf_rel_errors, load_weights, match_keypoints, orientation_boundary_shares, parity_report
 
 pytestmark = pytest.mark.gpu
 
@@ -569,4 +569,7 @@ def test_graf_1_to_6_application_counts(L, nets, mode):
     print("img1: %d of %d matched keypoints take another orientation bin than the oracle; their top-2 bin margins (oracle): %s" % (
         flipped.numel(), len(ia), ["%.1e" % margin[ia[i]].item() for i in flipped.tolist()]))
     assert len(ia) >= 0.995 * oL.shape[0] and flipped.numel() <= 0.005 * len(ia)
-    assert all(margin[ia[i]].item() < 5e-3 for i in flipped.tolist())
+    # ... or (tests/helpers.py::orientation_boundary_shares) own a pixel on a histogram-bin boundary that outweighs its bin margin: the reference
+    # adds a pixel's whole weight to the LOWER bin only, so such a pixel changes bins under any perturbation
+    _, share = orientation_boundary_shares(st["debug"]["ori"]["patches"])
+    assert all(margin[ia[i]].item() < 5e-3 or share[ia[i]].item() > margin[ia[i]].item() for i in flipped.tolist())

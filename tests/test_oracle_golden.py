@@ -158,6 +158,34 @@ def test_handcrafted_estimators_8f():
     assert (O.baumberg_shape(P) - T(z["A"])).abs().max() < 1e-6
 
 
+def test_orientation_histogram_has_bin_boundary_discontinuities():
+    """The accounting of the GPU application test (test_gpu_parity.py::test_graf_1_to_6_application_counts[hcori]) rests on this property of the
+    reference's gradient histogram: only the lower-bin weight of a pixel is accumulated, so a pixel ON a bin boundary switches bins under an
+    epsilon change.  (i) Constructed: a ramp patch whose gradient direction moves across a bin boundary by 2e-4 bins changes its histogram's mass 18x; (ii) in the graf img1 keypoints such pixels exist (helpers.orientation_boundary_shares finds a keypoint whose
+    boundary pixel outweighs its bin margin)."""
+    import math
+
+    from helpers import orientation_boundary_shares
+    # (i) a linear ramp: every interior pixel has the same gradient direction, 1e-4 bins below / above the boundary between bins 19 and 20
+    PS = 19
+    yy, xx = torch.meshgrid(torch.arange(PS, dtype=torch.float64), torch.arange(PS, dtype=torch.float64), indexing="ij")
+    hists = []
+    for eps in (-1e-4, 1e-4):
+        th = (2.0 * math.pi) * (20.0 + eps) / 36.0 - math.pi          # o_big = 20 +- 1e-4 bins
+        ramp = (-(xx * math.cos(th) + yy * math.sin(th)) * 3.0).float().view(1, 1, PS, PS)   # gx = 0.5 x[j-1] - 0.5 x[j+1] = 3 cos(th), gy = 3 sin(th)
+        hists.append(O.orientation_hist_bins(ramp)[0])
+    # below the boundary the interior's weight lands in bin 19 scaled by (1 - 0.9999); above it bin 20 takes all of it: the histogram's
+    # mass jumps 18x for a change of direction of 2e-4 bins
+    # (what is left below the boundary are the border pixels, whose replicate-padded gradients point elsewhere)
+    assert hists[1][20] > 10 * hists[0][20] and hists[1].sum() > 10 * hists[0].sum(), (hists[0], hists[1])
+    # (ii) graf img1, K = 3000 with hand-crafted orientation
+    f = gold("graf_full.npz")
+    _, _, st = O.detect(gray_from_rgb(f["rgb"]), W["affnet"], None, 3000, do_ori=True, debug=True)
+    margin, share = orientation_boundary_shares(st["debug"]["ori"]["patches"])
+    risky = ((share > margin) & (margin > 1e-2)).nonzero().view(-1)
+    assert margin.shape == (st["debug"]["ori"]["patches"].size(0),) and risky.numel() >= 1, risky
+
+
 def test_distance_matrix_vs_reference_if_present():
     """Losses.distance_matrix_vector against the live reference when /root/reference is mounted."""
     import ref_harness as R
